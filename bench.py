@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""Benchmark of the Fock-backend hot path (BASELINE.json metric: Fock amp-gate updates/s +
+achieved HBM GB/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--modes M]
+
+Workload (N = 1): BASELINE config 2 -- 8-mode pure state, cutoff 10 (1e8 complex128
+amplitudes, 1.6 GB), Sgate + Dgate on every mode and a random 8-mode rectangular
+interferometer = 80 gates (8 S + 8 D + 36 R + 28 BS).  A "step" is one pass of the whole
+circuit over the resident state.  One amp-gate update = one stored amplitude passing
+through one gate of the call list (fused or not), so a step is 80 x 1e8 updates.
+
+* ``value``: updates/s with the state resident in HBM, CUDA-event timed, max over ranks.
+* ``e2e``: the same metric through the reference-facing plugin API (``B200FockBackend``:
+  ``begin_circuit`` .. gate calls .. ``state()``) with host buffers: every step copies the
+  step's gate-parameter table from pinned host memory to the device and reads the
+  requested result (trace + a list of Fock probabilities) back to the host.
+* ``roofline``: the dominant kernel (k_apply_blocks) -- algorithmic bytes (32 B per
+  amplitude per pass) / CUDA-event time per launch, against MEASURED_PEAKS.json.
+* ``cpu_baseline``: the oracle port in the reference's loop structure
+  (oracle/fock_oracle.py, style="reference") on a bounded sample of the same workload.
+* ``--impl reference``: the reference arm -- the same oracle port timed on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "fock_amp_gate_updates_per_s"
+UNIT = "updates/s"
+
+
+# ------------------------------------------------------------------------------ helpers
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, reasons, smax = [], set(), None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                sm.append(float(f[1]))
+                smax = float(f[2])
+                for nm, v in zip(names, f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            busy = [x for x in sm if x >= 0.5 * max(sm)] or sm
+            out = {"sm_mhz": float(np.median(busy)), "sm_max_mhz": smax, "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+def cpu_reference_run(n_modes, D, steps, warmup):
+    """The oracle port (reference loop structure, numba selection-rule kernels) on the host:
+    one step = the config-2 circuit generator at ``n_modes`` modes."""
+    from oracle.fock_oracle import OracleBackend
+    from strawberryfields_b200 import workloads as W
+
+    calls = W.config2_circuit(n_modes, seed=42)
+    be = OracleBackend(style="reference")
+    be.begin_circuit(n_modes, cutoff_dim=D)
+    # numba JIT warm-up for this ndim (the reference pays 9-15 s per new signature)
+    W.run_calls(be, [c for c in calls if c[0] == "beamsplitter"][:2])
+    for _ in range(warmup):
+        be.reset()
+        W.run_calls(be, calls)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        be.reset()
+        W.run_calls(be, calls)
+    dt = time.perf_counter() - t0
+    updates = len(calls) * D ** n_modes * steps
+    return updates / dt, dt / steps, len(calls)
+
+
+def reference_arm(args):
+    """``--impl reference``: the reference algorithm's CPU port on this box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_modes, D = 6, 10
+    steps, warmup = max(1, min(args.steps, 3)), min(args.warmup, 1)
+    val, per_step, ngates = cpu_reference_run(n_modes, D, steps, warmup)
+    sample = "config-2 generator at %d modes, cutoff %d (%d amplitudes, %d gates) per step" % (
+        n_modes, D, D ** n_modes, ngates)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "complex128", "data": "synthetic",
+        "config": {"workload": "BASELINE config 2 (8-mode D=10 pure interferometer circuit); reference arm "
+                               "runs a bounded sample: " + sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                         "host_cores_available": os.cpu_count(),
+                         "note": "the reference fock backend is single-threaded (numba kernels without "
+                                 "parallel=True, D x D numpy); port = oracle/fock_oracle.py style='reference'"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------ b200 arm
+def b200_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    from strawberryfields_b200 import B200FockBackend, lib
+    from strawberryfields_b200 import workloads as W
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    handle = lib.load(build_if_missing=False)
+
+    n_modes, D = args.modes, args.cutoff
+    calls = W.config2_circuit(n_modes, seed=42 + rank)
+    elements = D ** n_modes
+    updates_per_step = len(calls) * elements
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident leg: `value` ---------------------------------------------------
+    be = B200FockBackend()
+    be.begin_circuit(n_modes, cutoff_dim=D)
+    for _ in range(args.warmup):
+        W.run_calls(be, calls)
+        be.circuit._flush()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    handle.b200_reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        W.run_calls(be, calls)
+        be.circuit._flush()
+    e1.record()
+    barrier()
+    launches = int(handle.b200_launch_count())
+    clocks = sampler.stop()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    value = updates_per_step * args.steps * world / (ms_total * 1e-3)
+
+    # ---- roofline leg: per-launch CUDA events on one more step ------------------------------
+    prof = []
+    be.circuit.profile = prof
+    W.run_calls(be, calls)
+    be.circuit._flush()
+    torch.cuda.synchronize()
+    be.circuit.profile = None
+    by_tag = {}
+    for tag, nbytes, a, b in prof:
+        t = a.elapsed_time(b) * 1e-3
+        d = by_tag.setdefault(tag, [0, 0.0, 0])
+        d[0] += nbytes
+        d[1] += t
+        d[2] += 1
+    dom = [(tag, v) for tag, v in by_tag.items() if tag.startswith("gate")]
+    dom_bytes = sum(v[0] for _, v in dom)
+    dom_time = sum(v[1] for _, v in dom)
+    dom_n = sum(v[2] for _, v in dom)
+    peak, peak_src = measured_peaks()
+    achieved = dom_bytes / dom_time / 1e9 if dom_time > 0 else 0.0
+    roofline = {
+        "kernel": "k_apply_blocks", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "launches_per_step": dom_n, "avg_launch_ms": dom_time / max(dom_n, 1) * 1e3,
+        "algorithmic_bytes_per_launch": 32 * elements,
+        "frac_of_nominal_8TBs": achieved / 8000.0,
+        "by_pass": {tag: {"launches": v[2], "GBps": v[0] / v[1] / 1e9} for tag, v in sorted(by_tag.items())},
+    }
+
+    # ---- end-to-end leg through the plugin API with host buffers: `e2e` -----------------------
+    # inputs: the step's gate-parameter table in pinned host memory, copied to the device and
+    # consumed there by the gate-table generators; result: trace + a list of Fock probabilities
+    # read back to the host.
+    from strawberryfields_b200 import DeviceParams
+
+    def params_of(c):
+        vals = [float(x) for x in c[1:] if isinstance(x, float)]
+        return (vals + [0.0, 0.0])[:2]
+
+    ptab = np.array([params_of(c) for c in calls], dtype=np.float64)
+    pinned = torch.from_numpy(ptab).pin_memory()
+    outcomes = [[0] * n_modes]
+    for m in range(n_modes):
+        for k in (1, 2):
+            o = [0] * n_modes
+            o[m] = k
+            outcomes.append(o)
+
+    def e2e_step():
+        dev_params = pinned.to("cuda", non_blocking=True)  # H2D of the step's inputs
+        be2 = B200FockBackend()
+        be2.begin_circuit(n_modes, cutoff_dim=D)
+        for i, c in enumerate(calls):
+            modes = [x for x in c[1:] if isinstance(x, int)]
+            getattr(be2, c[0])(*([DeviceParams(dev_params[i])] + ([None] if c[0] != "rotation" else []) + modes))
+        st = be2.state()
+        return np.array([st.trace()] + [st.fock_prob(o) for o in outcomes])  # D2H reads
+
+    for _ in range(min(args.warmup, 3)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    ms2 = torch.tensor([max(e0.elapsed_time(e1), wall * 1e3)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_value = updates_per_step * args.steps * world / (float(ms2.item()) * 1e-3)
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(ptab.nbytes),
+           "d2h_bytes_per_step": int(8 * (len(outcomes) + 1)),
+           "api": "B200FockBackend.begin_circuit/gates/state().trace()/fock_prob()"}
+
+    # ---- CPU baseline (rank 0, N = 1 only) -----------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, per_step, ngates = cpu_reference_run(6, 10, 1, 0)
+        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": "config-2 generator at 6 modes, cutoff 10 (1e6 amplitudes, %d gates), 1 step = %.1f s"
+                         % (ngates, per_step),
+               "host_cores_available": os.cpu_count()}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "complex128", "data": "synthetic",
+            "config": {
+                "workload": "BASELINE config 2: %d-mode pure state, cutoff %d (%.3g complex128 amplitudes), "
+                            "Sgate+Dgate per mode + random rectangular interferometer, %d gates per step"
+                            % (n_modes, D, elements, len(calls)),
+                "parallelism": "replicas x%d" % world if world > 1 else "single GPU",
+                "l2": "state %.2f GB per GPU > 126 MB L2: every pass streams from HBM" % (elements * 16 / 1e9),
+                "passes_per_step": sum(v[2] for v in by_tag.values()),
+            },
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+            "hbm_GBps_whole_step": 32 * elements * sum(v[2] for v in by_tag.values()) * args.steps
+                                   / (ms_total * 1e-3) / 1e9,
+            "circuit_ms": ms_total / args.steps,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--modes", type=int, default=8)
+    ap.add_argument("--cutoff", type=int, default=10)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,961 @@
+"""Device-resident Fock-basis circuit: the host-side driver of ``libb200fock.so``.
+
+Mirrors the interface of the reference's ``Circuit``
+(``/root/reference/strawberryfields/backends/fockbackend/circuit.py:35-812``): same method
+names, argument meaning and error behaviour, but the state lives in HBM and every
+update is a CUDA kernel launched through the C ABI (``include/b200fock.h``).  PyTorch
+is used only to own device memory and the stream.
+
+State layout (same as the reference, ``backend.py:50-56``): C-order complex128,
+``[B?][D]*n`` for pure states and ``[B?][D]*2n`` with axes ``(ket_0, bra_0, ket_1, ...)``
+for mixed states; ``B`` is an optional leading batch axis (TF-backend semantics,
+``tfbackend/backend.py:66-112``).
+
+Lazy gate queue.  The engine delivers gates one call at a time
+(``engine.py:422-457``); to let one HBM pass do the work of several gates the circuit
+keeps, per mode, one pending single-mode operator:
+
+* consecutive single-mode gates on a mode are pre-multiplied (D x D products on the
+  device);
+* diagonal gates (``Rgate``, ``Kgate``) are folded into the neighbouring dense or
+  two-mode gate table and cost no pass at all;
+* whatever is still pending when the state is observed is flushed -- all leftover
+  diagonals in ONE multi-axis pass.
+"""
+from __future__ import annotations
+
+import copy
+import ctypes as C
+from math import factorial
+
+import numpy as np
+import torch
+
+from . import lib as L
+
+C128 = np.complex128
+_HBAR = 2  # circuit.py:61
+
+# Set (together with a stand-in library handle) ONLY by the CPU test-suite, which drives the host
+# logic against a numpy double of the C ABI (tests/fake_lib.py).  The product never sets it.
+_TEST_HOST_MODE = False
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class DeviceParams:
+    """Gate parameters that already live on the device: a contiguous float64 tensor of shape
+    ``(2,)`` or ``(2, nbatch)`` (row 0 = first parameter, row 1 = second).  Pass it as the
+    first parameter of a gate call (the second is ignored); the gate table is generated on
+    the device straight from it, so no parameter ever returns to the host."""
+
+    def __init__(self, tensor):
+        if tensor.dtype != torch.float64 or not tensor.is_contiguous() or tensor.shape[0] != 2:
+            raise ValueError("DeviceParams needs a contiguous float64 tensor of shape (2,) or (2, nbatch)")
+        self.tensor = tensor
+        self.nbatch = 1 if tensor.dim() == 1 else int(tensor.shape[1])
+
+
+class DeviceCircuit:
+    """GPU mirror of ``fockbackend.circuit.Circuit``."""
+
+    def __init__(self, num, trunc, pure=True, batch_size=None, device=None, strict_purity=False,
+                 fuse=True):
+        if num < 0:
+            raise ValueError("Number of modes must be non-negative -- got {}".format(num))
+        if trunc <= 0:
+            raise ValueError("Truncation must be positive -- got {}".format(trunc))
+        if trunc > L.MAX_CUTOFF:
+            raise ValueError("b200fock supports cutoff_dim <= {}".format(L.MAX_CUTOFF))
+        L.load()  # fail loudly when the CUDA library is missing
+        if _TEST_HOST_MODE:
+            self.device = torch.device("cpu")
+        else:
+            if not torch.cuda.is_available():
+                raise L.B200Error("b200fock needs a CUDA device (there is no CPU fallback)")
+            self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self._num_modes = num
+        self._hbar = _HBAR
+        self._batched = batch_size is not None
+        self._B = int(batch_size) if batch_size is not None else 1
+        if self._B < 1:
+            raise ValueError("batch_size must be a positive integer")
+        self._strict = bool(strict_purity)
+        self._fuse = bool(fuse)
+        self._scratch = None
+        self._part = None
+        self._norm_out = torch.zeros(2, dtype=torch.float64, device=self.device)
+        self._norm_part = torch.zeros(4096, dtype=torch.float64, device=self.device)
+        self.reset(pure=pure, cutoff_dim=trunc)
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self):
+        if self.device.type != "cuda":
+            return None
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _axes(self):
+        return self._num_modes if self._pure else 2 * self._num_modes
+
+    def _size(self):
+        """elements per batch entry"""
+        return self._trunc ** self._axes()
+
+    def _stride(self, axis, naxes=None):
+        naxes = self._axes() if naxes is None else naxes
+        return self._trunc ** (naxes - 1 - axis)
+
+    def _new(self, n):
+        return torch.empty(int(n), dtype=torch.complex128, device=self.device)
+
+    def _get_scratch(self, n):
+        if self._scratch is None or self._scratch.numel() < n:
+            self._scratch = None
+            self._scratch = self._new(n)
+        return self._scratch[:n] if self._scratch.numel() != n else self._scratch
+
+    def _get_part(self, n_out):
+        need = int(n_out) * 64
+        if self._part is None or self._part.numel() < need:
+            self._part = self._new(need)
+        return self._part
+
+    def _own(self):
+        """Copy-on-write: a state object returned by ``snapshot()`` shares the buffer until the
+        circuit is modified again."""
+        if self._shared:
+            self._buf = self._buf.clone()
+            self._shared = False
+
+    def snapshot(self):
+        """Read-only view of the current state for a state object (no copy now)."""
+        self._flush()
+        snap = object.__new__(DeviceCircuit)
+        snap.__dict__.update(self.__dict__)
+        snap._pending = {}
+        snap._untouched = set()
+        snap._scratch = None
+        snap._part = None
+        snap._norm_part = torch.zeros(4096, dtype=torch.float64, device=self.device)
+        snap._shared = True
+        self._shared = True
+        return snap
+
+    @classmethod
+    def from_buffer(cls, like, buf, num_modes, pure):
+        """Wrap an existing device tensor (e.g. a reduced density matrix) as a circuit."""
+        obj = object.__new__(cls)
+        obj.__dict__.update(like.__dict__)
+        obj._buf = buf
+        obj._num_modes = num_modes
+        obj._pure = pure
+        obj._pending = {}
+        obj._untouched = set()
+        obj._scratch = None
+        obj._part = None
+        obj._norm_part = torch.zeros(4096, dtype=torch.float64, device=like.device)
+        obj._shared = False
+        return obj
+
+    def permute_modes(self, perm):
+        """New mode p <- old mode perm[p] (both tensor axes of a mode move together)."""
+        self._flush()
+        D, B, n = self._trunc, self._B, self._num_modes
+        per = self._size()
+        out = self._new(self._buf.numel())
+        oa = [(B, per, 0, per)] if B > 1 else []
+        for p in range(n):
+            for t, ax in enumerate(self._mode_axes(p)):
+                oa.append((D, self._stride(self._mode_axes(int(perm[p]))[t]), 0, self._stride(ax)))
+        self._gather(self._buf, None, out, oa)
+        self._buf, self._shared, self._scratch = out, False, None
+
+    def _vacuum(self, buf, per):
+        L.call("b200_fill_zero", _ptr(buf), buf.numel(), self._stream())
+        for b in range(self._B):
+            L.call("b200_set_element", _ptr(buf), b * per, 1.0, 0.0, self._stream())
+
+    # ------------------------------------------------------------------ reset (circuit.py:89-116)
+    def reset(self, pure=None, cutoff_dim=None, num_subsystems=None):
+        if pure is not None:
+            if not isinstance(pure, bool):
+                raise ValueError("Argument 'pure' must be either True or False")
+            self._pure = pure
+        if num_subsystems is not None:
+            if not isinstance(num_subsystems, int):
+                raise ValueError("Argument 'num_subsystems' must be a positive integer")
+            self._num_modes = num_subsystems
+        if cutoff_dim is not None:
+            if not isinstance(cutoff_dim, int) or cutoff_dim < 1:
+                raise ValueError("Argument 'cutoff_dim' must be a positive integer")
+            if cutoff_dim > L.MAX_CUTOFF:
+                raise ValueError("b200fock supports cutoff_dim <= {}".format(L.MAX_CUTOFF))
+            self._trunc = cutoff_dim
+        self._scratch = None
+        self._buf = None
+        self._shared = False
+        per = self._size()
+        self._buf = self._new(self._B * per)
+        self._vacuum(self._buf, per)
+        self._pending = {}
+        self._untouched = set(range(self._num_modes))
+
+    # ------------------------------------------------------------------ gate tables
+    def _params(self, *ps):
+        """scalars or length-B arrays -> (nbatch, scalars, device params or None)"""
+        if isinstance(ps[0], DeviceParams):
+            if ps[0].nbatch not in (1, self._B):
+                raise ValueError("DeviceParams batch does not match the circuit's batch_size")
+            return ps[0].nbatch, [0.0, 0.0], ps[0].tensor
+        arrs = [np.asarray(p, dtype=np.float64) for p in ps]
+        if all(a.ndim == 0 for a in arrs):
+            return 1, [float(a) for a in arrs] + [0.0] * (2 - len(arrs)), None
+        if not self._batched:
+            raise ValueError("array-valued gate parameters need a batched circuit (batch_size=...)")
+        full = np.zeros((2, self._B), dtype=np.float64)
+        for i, a in enumerate(arrs):
+            if a.ndim == 0:
+                full[i, :] = float(a)
+            elif a.shape == (self._B,):
+                full[i, :] = a
+            else:
+                raise ValueError("gate parameter must be a scalar or have shape (batch_size,)")
+        dev = torch.from_numpy(full).to(self.device)
+        return self._B, [0.0, 0.0], dev
+
+    def _gen1(self, kind, p0, p1):
+        nb, sc, dev = self._params(p0, p1)
+        D = self._trunc
+        out = self._new(nb * D * D)
+        L.call("b200_gen_gate1", kind, D, nb, sc[0], sc[1], _ptr(dev), _ptr(out), self._stream())
+        return out.view(nb, D, D)
+
+    def _gen_diag(self, kind, p0):
+        nb, sc, dev = self._params(p0)
+        D = self._trunc
+        per = D * D if kind == L.DIAG_CROSS_KERR else D
+        out = self._new(nb * per)
+        L.call("b200_gen_diag", kind, D, nb, sc[0], _ptr(dev), _ptr(out), self._stream())
+        return out.view(nb, per)
+
+    def _gen2(self, kind, p0, p1=0.0):
+        nb, sc, dev = self._params(p0, p1)
+        D = self._trunc
+        P = L.packed_size(D)
+        out = self._new(nb * P)
+        L.call("b200_gen_gate2", kind, D, nb, sc[0], sc[1], _ptr(dev), _ptr(out), self._stream())
+        return out.view(nb, P)
+
+    def _upload_matrix(self, mat):
+        mat = np.ascontiguousarray(np.asarray(mat, dtype=C128))
+        D = self._trunc
+        if mat.shape != (D, D):
+            raise ValueError("single-mode operator must have shape (cutoff, cutoff)")
+        return torch.from_numpy(mat).to(self.device).view(1, D, D)
+
+    @staticmethod
+    def _expand(t, nb):
+        return t if t.shape[0] == nb else t.expand(nb, *t.shape[1:]).contiguous()
+
+    # ------------------------------------------------------------------ raw kernels
+    def _pass(self, tag, name, *args):
+        """Launch one full pass over the state.  With ``self.profile`` set to a list, the
+        launch is bracketed by CUDA events on the launching stream and
+        ``(tag, algorithmic bytes, start, end)`` is appended (bench.py's roofline leg)."""
+        prof = self.__dict__.get("profile")
+        if prof is None:
+            L.call(name, *args)
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.call(name, *args)
+        e1.record()
+        prof.append((tag, 32 * self._B * self._size(), e0, e1))
+
+    def _k_gate1(self, U, axis, conj):
+        self._own()
+        D, B = self._trunc, self._B
+        naxes = self._axes()
+        nb = U.shape[0]
+        self._pass("gate1/axis%d" % (naxes - 1 - axis), "b200_apply_gate1", _ptr(self._buf), D ** axis, D, D ** (naxes - 1 - axis), _ptr(U),
+               int(conj), B, self._size(), D * D if nb > 1 else 0, self._stream())
+
+    def _k_gate2(self, G, rule, ax1, ax2, conj):
+        self._own()
+        D, B = self._trunc, self._B
+        nb = G.shape[0]
+        naxes = self._axes()
+        self._pass("gate2/rule%d/axes%d,%d" % (rule, naxes - 1 - ax1, naxes - 1 - ax2), "b200_apply_gate2",
+                   _ptr(self._buf), self._size(), D, self._stride(ax1), self._stride(ax2),
+               rule, _ptr(G), int(conj), B, self._size(), G.shape[1] if nb > 1 else 0, self._stream())
+
+    def _k_diag_pair(self, tab, ax1, ax2, conj):
+        self._own()
+        D, B = self._trunc, self._B
+        nb = tab.shape[0]
+        self._pass("diag2", "b200_apply_diag", _ptr(self._buf), self._size(), D, self._stride(ax1), self._stride(ax2),
+               _ptr(tab), int(conj), B, self._size(), tab.shape[1] if nb > 1 else 0, self._stream())
+
+    def _k_diag_multi(self, items):
+        """items: list of (table [nb, D], mode) -- one pass for all of them."""
+        self._own()
+        D, B = self._trunc, self._B
+        axes = []  # (stride, conj, table)
+        for tab, mode in items:
+            if self._pure:
+                axes.append((self._stride(mode), 0, tab))
+            else:
+                axes.append((self._stride(2 * mode), 0, tab))
+                axes.append((self._stride(2 * mode + 1), 1, tab))
+        for i in range(0, len(axes), L.MAX_AXES):
+            chunk = axes[i:i + L.MAX_AXES]
+            nb = max(t.shape[0] for _, _, t in chunk)
+            tabs = torch.stack([self._expand(t, nb) for _, _, t in chunk], dim=1).contiguous()
+            k = len(chunk)
+            strides = (C.c_int64 * k)(*[s for s, _, _ in chunk])
+            conjs = (C.c_int * k)(*[c for _, c, _ in chunk])
+            self._pass("diag_multi/%d" % k, "b200_apply_diag_multi", _ptr(self._buf), self._size(), D, k, strides, conjs, _ptr(tabs),
+                   B, self._size(), k * D if nb > 1 else 0, self._stream())
+
+    # ------------------------------------------------------------------ immediate application
+    def _apply_dense_now(self, U, mode):
+        if self._pure:
+            self._k_gate1(U, mode, 0)
+        else:
+            self._k_gate1(U, 2 * mode, 0)
+            self._k_gate1(U, 2 * mode + 1, 1)
+
+    def _apply_pair_now(self, G, rule, m1, m2):
+        if self._pure:
+            self._k_gate2(G, rule, m1, m2, 0)
+        else:
+            self._k_gate2(G, rule, 2 * m1, 2 * m2, 0)
+            self._k_gate2(G, rule, 2 * m1 + 1, 2 * m2 + 1, 1)
+
+    # ------------------------------------------------------------------ lazy queue
+    def _touch(self, *modes):
+        for m in modes:
+            self._untouched.discard(m)
+
+    def _queue_dense(self, U, mode):
+        self._touch(mode)
+        if not self._fuse:
+            self._apply_dense_now(U, mode)
+            return
+        D = self._trunc
+        pend = self._pending.get(mode)
+        if pend is None:
+            self._pending[mode] = ("dense", U)
+        elif pend[0] == "diag":
+            d = pend[1]
+            nb = max(U.shape[0], d.shape[0])
+            U = self._expand(U, nb)  # freshly generated table: folding in place is safe
+            L.call("b200_fold_diag_gate1", D, nb, _ptr(U), _ptr(self._expand(d, nb)), None, self._stream())
+            self._pending[mode] = ("dense", U)
+        else:
+            P = pend[1]
+            nb = max(U.shape[0], P.shape[0])
+            out = self._new(nb * D * D).view(nb, D, D)
+            L.call("b200_compose_gate1", D, nb, _ptr(self._expand(U, nb)), _ptr(self._expand(P, nb)),
+                   _ptr(out), self._stream())
+            self._pending[mode] = ("dense", out)
+
+    def _queue_diag(self, d, mode):
+        self._touch(mode)
+        if not self._fuse:
+            self._k_diag_multi([(d, mode)])
+            return
+        D = self._trunc
+        pend = self._pending.get(mode)
+        if pend is None:
+            self._pending[mode] = ("diag", d)
+        elif pend[0] == "diag":
+            nb = max(d.shape[0], pend[1].shape[0])
+            out = self._new(nb * D).view(nb, D)
+            L.call("b200_mul_tables", nb * D, _ptr(self._expand(d, nb)), _ptr(self._expand(pend[1], nb)), 0,
+                   _ptr(out), self._stream())
+            self._pending[mode] = ("diag", out)
+        else:
+            P = pend[1]
+            nb = max(d.shape[0], P.shape[0])
+            P = self._expand(P, nb).clone()
+            L.call("b200_fold_diag_gate1", D, nb, _ptr(P), None, _ptr(self._expand(d, nb)), self._stream())
+            self._pending[mode] = ("dense", P)
+
+    def _flush(self, modes=None):
+        """Apply pending single-mode operators of ``modes`` (default: all)."""
+        if not self._pending:
+            return
+        keys = sorted(self._pending) if modes is None else [m for m in modes if m in self._pending]
+        diags = []
+        for m in keys:
+            kind, tab = self._pending.pop(m)
+            if kind == "dense":
+                self._apply_dense_now(tab, m)
+            else:
+                diags.append((tab, m))
+        if diags:
+            self._k_diag_multi(diags)
+
+    def _pair_gate(self, G, rule, m1, m2):
+        """Two-mode gate: pending diagonals on its modes are folded into the table,
+        pending dense operators are flushed first."""
+        self._touch(m1, m2)
+        D = self._trunc
+        pre = [None, None]
+        for i, m in enumerate((m1, m2)):
+            pend = self._pending.get(m)
+            if pend is None:
+                continue
+            if pend[0] == "diag":
+                pre[i] = self._pending.pop(m)[1]
+            else:
+                self._flush([m])
+        if pre[0] is not None or pre[1] is not None:
+            nb = max([G.shape[0]] + [p.shape[0] for p in pre if p is not None])
+            G = self._expand(G, nb).clone()
+            p1 = self._expand(pre[0], nb) if pre[0] is not None else None
+            p2 = self._expand(pre[1], nb) if pre[1] is not None else None
+            L.call("b200_fold_diag_gate2", rule, D, nb, _ptr(G), _ptr(p1), _ptr(p2), None, None, self._stream())
+        self._apply_pair_now(G, rule, m1, m2)
+
+    # ------------------------------------------------------------------ named gates (circuit.py:537-598)
+    def phase_shift(self, theta, mode):
+        self._queue_diag(self._gen_diag(L.DIAG_ROTATION, theta), mode)
+
+    def kerr_interaction(self, kappa, mode):
+        self._queue_diag(self._gen_diag(L.DIAG_KERR, kappa), mode)
+
+    def displacement(self, r, phi, mode):
+        self._queue_dense(self._gen1(L.GATE_DISPLACEMENT, r, phi), mode)
+
+    def squeeze(self, r, theta, mode):
+        self._queue_dense(self._gen1(L.GATE_SQUEEZE, r, theta), mode)
+
+    def cubic_phase_shift(self, gamma, mode):
+        """expm of the truncated x^3 (fockbackend/ops.py:296-306) is a host-built D x D
+        matrix; it is applied with the generic dense kernel."""
+        from scipy.linalg import expm
+
+        D = self._trunc
+        a = np.diag(np.sqrt(np.arange(1, D)), 1).astype(C128)
+        x = (a + a.conj().T) * np.sqrt(self._hbar / 2)
+        self._queue_dense(self._upload_matrix(expm(1j * float(gamma) / (3 * self._hbar) * (x @ x @ x))), mode)
+
+    def apply_matrix(self, mat, mode):
+        """Arbitrary single-mode operator (host matrix [out, in])."""
+        self._queue_dense(self._upload_matrix(mat), mode)
+
+    def beamsplitter(self, theta, phi, mode1, mode2):
+        self._pair_gate(self._gen2(L.GATE_BEAMSPLITTER, theta, phi), L.RULE_SUM, mode1, mode2)
+
+    def mzgate(self, phi_in, phi_ex, mode1, mode2):
+        self._pair_gate(self._gen2(L.GATE_MZ, phi_in, phi_ex), L.RULE_SUM, mode1, mode2)
+
+    def two_mode_squeeze(self, r, theta, mode1, mode2):
+        self._pair_gate(self._gen2(L.GATE_S2, r, theta), L.RULE_DIFF, mode1, mode2)
+
+    def cross_kerr_interaction(self, kappa, mode1, mode2):
+        # diagonal in both modes: commutes with pending diagonals, not with pending dense gates
+        self._touch(mode1, mode2)
+        self._flush([m for m in (mode1, mode2) if self._pending.get(m, ("", 0))[0] == "dense"])
+        tab = self._gen_diag(L.DIAG_CROSS_KERR, kappa)
+        if self._pure:
+            self._k_diag_pair(tab, mode1, mode2, 0)
+        else:
+            self._k_diag_pair(tab, 2 * mode1, 2 * mode2, 0)
+            self._k_diag_pair(tab, 2 * mode1 + 1, 2 * mode2 + 1, 1)
+
+    # ------------------------------------------------------------------ channels (circuit.py:65-87, 617-621)
+    def loss(self, T, mode):
+        self._flush([mode])  # operators pending on other modes commute with this channel
+        self._touch(mode)
+        self._to_mixed()
+        G = self._gen2(L.CHANNEL_LOSS, T)
+        self._k_gate2(G, L.RULE_DIFF, 2 * mode, 2 * mode + 1, 0)
+
+    # ------------------------------------------------------------------ strided gather wrapper
+    def _gather(self, A, B, Cout, out_axes, red_axes=(), flags=0, base=(0, 0, 0)):
+        """out_axes: [(ext, sa, sb, sc)], red_axes: [(ext, ta, tb)] (C order, last fastest)."""
+        def merge(axes, width):
+            axes = [a for a in axes if a[0] != 1]
+            out = []
+            for a in axes:
+                if out:
+                    p = out[-1]
+                    if all(p[i] == a[i] * a[0] for i in range(1, width)) and p[0] * a[0] < 2 ** 31:
+                        out[-1] = (p[0] * a[0],) + tuple(a[1:])
+                        continue
+                out.append(tuple(a))
+            return out
+
+        oa, ra = merge(list(out_axes), 4), merge(list(red_axes), 3)
+        if len(oa) > L.MAX_AXES or len(ra) > L.MAX_AXES:
+            raise L.B200Error("tensor rank exceeds the gather kernel's limit")
+        d = L.GatherDesc()
+        d.n_out_axes, d.n_red_axes = len(oa), len(ra)
+        for j, (e, sa, sb, sc) in enumerate(oa):
+            d.out_ext[j], d.out_sa[j], d.out_sb[j], d.out_sc[j] = e, sa, sb, sc
+        for j, (e, ta, tb) in enumerate(ra):
+            d.red_ext[j], d.red_ta[j], d.red_tb[j] = e, ta, tb
+        d.base_a, d.base_b, d.base_c = base
+        n_out = 1
+        for a in oa:
+            n_out *= a[0]
+        part = self._get_part(n_out) if (ra and n_out < 2 ** 16) else None
+        L.call("b200_gather_reduce", C.byref(d), _ptr(A), _ptr(B), _ptr(Cout), flags, _ptr(part), self._stream())
+
+    def _mode_axes(self, mode):
+        """state axes of a mode: (ket,) or (ket, bra)"""
+        return (mode,) if self._pure else (2 * mode, 2 * mode + 1)
+
+    # ------------------------------------------------------------------ pure -> mixed (ops.py:110-120)
+    def _to_mixed(self):
+        if not self._pure:
+            return
+        self._flush()
+        n, D, B = self._num_modes, self._trunc, self._B
+        per_p, per_m = D ** n, D ** (2 * n)
+        new = self._new(B * per_m)
+        axes = [(B, per_p, per_p, per_m)] if B > 1 else []
+        for i in range(n):
+            st = D ** (n - 1 - i)
+            axes.append((D, st, 0, D ** (2 * n - 1 - 2 * i)))
+            axes.append((D, 0, st, D ** (2 * n - 2 - 2 * i)))
+        self._gather(self._buf, self._buf, new, axes, flags=L.FLAG_CONJ_B)
+        self._buf = new
+        self._shared = False
+        self._scratch = None
+        self._pure = False
+
+    # ------------------------------------------------------------------ norm (circuit.py:367-371)
+    def _norm_device(self):
+        """squared norm (pure) or trace (mixed) per batch entry, as a device float64 tensor [B]."""
+        self._flush()
+        B, per = self._B, self._size()
+        out = torch.zeros(B, dtype=torch.float64, device=self.device)
+        if self._pure:
+            for b in range(B):
+                L.call("b200_norm2", C.c_void_p(self._buf.data_ptr() + 16 * b * per), per,
+                       C.c_void_p(out.data_ptr() + 8 * b), _ptr(self._norm_part), self._stream())
+        else:
+            n, D = self._num_modes, self._trunc
+            red = [(D, self._stride(2 * i) + self._stride(2 * i + 1), 0) for i in range(n)]
+            oa = [(B, per, 0, 1)] if B > 1 else []
+            self._gather(self._buf, None, out, oa, red, flags=L.FLAG_REAL_OUT)
+        return out
+
+    def norm(self):
+        v = self._norm_device().cpu().numpy()
+        v = np.sqrt(v) if self._pure else v
+        return v if self._batched else v[0]
+
+    # ------------------------------------------------------------------ modes (circuit.py:373-391)
+    def alloc(self, n=1):
+        self._flush()
+        D, B = self._trunc, self._B
+        k = self._axes()
+        add = n if self._pure else 2 * n
+        old_per, new_per = D ** k, D ** (k + add)
+        new = self._new(B * new_per)
+        L.call("b200_fill_zero", _ptr(new), new.numel(), self._stream())
+        axes = [(B, old_per, 0, new_per)] if B > 1 else []
+        axes.append((old_per, 1, 0, D ** add))
+        self._gather(self._buf, None, new, axes)
+        self._buf = new
+        self._shared = False
+        self._scratch = None
+        for m in range(self._num_modes, self._num_modes + n):
+            self._untouched.add(m)
+        self._num_modes += n
+
+    def dealloc(self, modes):
+        self._to_mixed()
+        self._flush()
+        keep = [m for m in range(self._num_modes) if m not in modes]
+        self._buf = self._partial_trace_keep(keep)
+        self._shared = False
+        self._scratch = None
+        self._num_modes = len(keep)
+        self._untouched = set()
+        self._pending = {}
+
+    def _partial_trace_keep(self, keep):
+        """mixed state -> mixed state on the (sorted) modes ``keep`` (ops.py:144-157)."""
+        n, D, B = self._num_modes, self._trunc, self._B
+        k = len(keep)
+        per, new_per = D ** (2 * n), D ** (2 * k)
+        out = self._new(B * new_per)
+        oa = [(B, per, 0, new_per)] if B > 1 else []
+        for j, m in enumerate(keep):
+            oa.append((D, self._stride(2 * m), 0, D ** (2 * k - 1 - 2 * j)))
+            oa.append((D, self._stride(2 * m + 1), 0, D ** (2 * k - 2 - 2 * j)))
+        red = [(D, self._stride(2 * m) + self._stride(2 * m + 1), 0) for m in range(n) if m not in keep]
+        self._gather(self._buf, None, out, oa, red)
+        return out
+
+    # ------------------------------------------------------------------ preparation (circuit.py:393-535)
+    def prepare_multimode(self, state, modes):
+        if isinstance(modes, int):
+            modes = [modes]
+        modes = list(modes)
+        if self._batched:
+            raise NotImplementedError("state preparation on a batched b200fock circuit is not supported yet")
+        self._flush()
+        D, n, k = self._trunc, self._num_modes, len(modes)
+        pure_shape, mixed_shape = (D,) * k, (D,) * (2 * k)
+        state = np.asarray(state)
+        if state.shape == (D ** k,):
+            state = state.reshape(pure_shape)
+        elif state.shape == (D ** k, D ** k):
+            state = state.reshape(mixed_shape)
+        if state.shape != pure_shape and state.shape != mixed_shape:
+            raise ValueError("Incorrect shape for state preparation")
+        if len(modes) != len(set(modes)):
+            raise ValueError("The specified modes cannot appear multiple times.")
+        is_ket = state.shape == pure_shape
+        host = np.ascontiguousarray(state.astype(C128))
+
+        if n == k:
+            # circuit.py:441-444 fast path (+ the mode permutation of 461-473)
+            self._pure = bool(is_ket)
+            src = torch.from_numpy(host.reshape(-1)).to(self.device)
+            if modes == list(range(n)):
+                self._buf = src
+            else:
+                self._buf = self._new(src.numel())
+                naxes = self._axes()
+                oa = []
+                for f in range(n):
+                    j = modes.index(f)
+                    for t, ax in enumerate(self._mode_axes(f)):
+                        src_axis = j if self._pure else 2 * j + t
+                        oa.append((D, D ** (naxes - 1 - src_axis), 0, self._stride(ax)))
+                self._gather(src, None, self._buf, oa)
+            self._shared = False
+            self._scratch = None
+            self._untouched = set()
+            return
+
+        if (self._pure and is_ket and not self._strict
+                and all(m in self._untouched for m in modes)):
+            # Modes still in the untouched product vacuum: psi = psi_rest (x) |0..0>, so replacing them
+            # keeps the state pure (the reference would switch to a D^2n tensor here).
+            src = torch.from_numpy(host.reshape(-1)).to(self.device)
+            out = self._new(self._buf.numel())
+            oa = []
+            for f in range(n):
+                if f in modes:
+                    j = modes.index(f)
+                    oa.append((D, 0, D ** (k - 1 - j), self._stride(f)))
+                else:
+                    oa.append((D, self._stride(f), 0, self._stride(f)))
+            self._gather(self._buf, src, out, oa)
+            self._buf = out
+            self._shared = False
+            self._scratch = None
+            self._touch(*modes)
+            return
+
+        # general case: rho <- Tr_modes(rho) (x) new, written straight into its final axis order
+        self._to_mixed()
+        if is_ket:
+            host = np.multiply.outer(host, host.conj()).transpose(
+                [x for i in range(k) for x in (i, k + i)]).copy() if k else host
+        src = torch.from_numpy(np.ascontiguousarray(host).reshape(-1)).to(self.device)
+        keep = [m for m in range(n) if m not in modes]
+        red = self._partial_trace_keep(keep)
+        kk = len(keep)
+        out = self._new(D ** (2 * n))
+        oa = []
+        for f in range(n):
+            for t in (0, 1):
+                sc = D ** (2 * n - 1 - (2 * f + t))
+                if f in modes:
+                    j = modes.index(f)
+                    oa.append((D, 0, D ** (2 * k - 1 - (2 * j + t)), sc))
+                else:
+                    j = keep.index(f)
+                    oa.append((D, D ** (2 * kk - 1 - (2 * j + t)), 0, sc))
+        self._gather(red, src, out, oa)
+        self._buf = out
+        self._shared = False
+        self._scratch = None
+        self._touch(*modes)
+
+    def prepare(self, state, mode):
+        self.prepare_multimode(state, [mode] if isinstance(mode, int) else mode)
+
+    def _prepare_ket(self, ket, mode):
+        if self._pure:
+            self.prepare(ket, mode)
+        else:
+            self.prepare(np.outer(ket, ket.conj()), mode)
+
+    # single-mode kets: fockbackend/ops.py:383-461 (tiny host vectors)
+    def prepare_mode_fock(self, n, mode):
+        v = np.zeros(self._trunc, dtype=C128)
+        v[n] = 1.0
+        self._prepare_ket(v, mode)
+
+    def prepare_mode_coherent(self, r, phi, mode):
+        self._prepare_ket(_coherent(r, phi, self._trunc), mode)
+
+    def prepare_mode_squeezed(self, r, theta, mode):
+        self._prepare_ket(_squeezed(r, theta, self._trunc), mode)
+
+    def prepare_mode_displaced_squeezed(self, r_d, phi_d, r_s, phi_s, mode):
+        self._prepare_ket(_displaced_squeezed(r_d, phi_d, r_s, phi_s, self._trunc), mode)
+
+    def prepare_mode_thermal(self, nbar, mode):
+        D = self._trunc
+        if nbar == 0:
+            st = np.zeros((D, D), dtype=C128)
+            st[0, 0] = 1.0
+        else:
+            st = np.diag([nbar ** n / (nbar + 1) ** (n + 1) for n in range(D)]).astype(C128)
+        self.prepare(st, mode)
+
+    # ------------------------------------------------------------------ queries
+    def is_vacuum(self, tol):
+        """circuit.py:600-609"""
+        self._flush()
+        per = self._size()
+        v = self._buf[::per].cpu().numpy() if self._B > 1 else self._buf[:1].cpu().numpy()
+        fid = np.abs(v) ** 2 if self._pure else v
+        res = np.abs(fid - 1) <= tol
+        return res if self._batched else bool(res[0])
+
+    def get_state(self):
+        """(device tensor snapshot, pure) -- the reference returns its live array
+        (circuit.py:611-615); later gates mutate device memory, so this is a copy."""
+        self._flush()
+        return self._buf.clone(), self._pure
+
+    def host_state(self):
+        self._flush()
+        arr = self._buf.cpu().numpy()
+        shape = ([self._B] if self._batched else []) + [self._trunc] * self._axes()
+        return arr.reshape(shape)
+
+    # ------------------------------------------------------------------ reductions
+    def fock_probs_device(self):
+        """all_fock_probs (states.py:580-608) as a device float64 tensor [B, D^n]."""
+        self._flush()
+        n, D, B = self._num_modes, self._trunc, self._B
+        out = torch.empty(B * D ** n, dtype=torch.float64, device=self.device)
+        if self._pure:
+            L.call("b200_abs2", _ptr(self._buf), _ptr(out), self._buf.numel(), self._stream())
+        else:
+            oa = [(B, self._size(), 0, D ** n)] if B > 1 else []
+            for i in range(n):
+                oa.append((D, self._stride(2 * i) + self._stride(2 * i + 1), 0, D ** (n - 1 - i)))
+            self._gather(self._buf, None, out, oa, flags=L.FLAG_REAL_OUT)
+        return out.view(B, -1)
+
+    def marginal_probs_device(self, keep):
+        """Photon-number distribution of the (sorted) modes ``keep``: float64 [B, D^k].
+        Never forms D^(2n) for pure states (the reference does, circuit.py:632-635,675-677)."""
+        self._flush()
+        n, D, B = self._num_modes, self._trunc, self._B
+        k = len(keep)
+        out = torch.empty(B * D ** k, dtype=torch.float64, device=self.device)
+        per = self._size()
+        if self._pure:
+            oa = [(B, per, per, D ** k)] if B > 1 else []
+            for j, m in enumerate(keep):
+                oa.append((D, self._stride(m), self._stride(m), D ** (k - 1 - j)))
+            red = [(D, self._stride(m), self._stride(m)) for m in range(n) if m not in keep]
+            self._gather(self._buf, self._buf, out, oa, red, flags=L.FLAG_CONJ_B | L.FLAG_REAL_OUT)
+        else:
+            oa = [(B, per, 0, D ** k)] if B > 1 else []
+            for j, m in enumerate(keep):
+                oa.append((D, self._stride(2 * m) + self._stride(2 * m + 1), 0, D ** (k - 1 - j)))
+            red = [(D, self._stride(2 * m) + self._stride(2 * m + 1), 0) for m in range(n) if m not in keep]
+            self._gather(self._buf, None, out, oa, red, flags=L.FLAG_REAL_OUT)
+        return out.view(B, -1)
+
+    def reduced_dm_device(self, keep):
+        """Reduced density matrix of the (sorted) modes ``keep`` -> complex128 [B, D^2k]
+        with interleaved (ket, bra) axes (backend.py:219-253, states.py:613-642)."""
+        self._flush()
+        if not self._pure:
+            return self._partial_trace_keep(keep).view(self._B, -1)
+        n, D, B = self._num_modes, self._trunc, self._B
+        k = len(keep)
+        per, new_per = D ** n, D ** (2 * k)
+        out = self._new(B * new_per)
+        oa = [(B, per, per, new_per)] if B > 1 else []
+        for j, m in enumerate(keep):
+            oa.append((D, self._stride(m), 0, D ** (2 * k - 1 - 2 * j)))
+            oa.append((D, 0, self._stride(m), D ** (2 * k - 2 - 2 * j)))
+        red = [(D, self._stride(m), self._stride(m)) for m in range(n) if m not in keep]
+        self._gather(self._buf, self._buf, out, oa, red, flags=L.FLAG_CONJ_B)
+        return out.view(B, -1)
+
+    # ------------------------------------------------------------------ Fock measurement (circuit.py:623-711)
+    def _project_reset(self, modes, values):
+        """|0..0><x| on ``modes`` (ops.py:179-198), out of place."""
+        D = self._trunc
+        out = self._get_scratch(self._buf.numel())
+        L.call("b200_fill_zero", _ptr(out), out.numel(), self._stream())
+        base_a = 0
+        for m, v in zip(modes, values):
+            for ax in self._mode_axes(m):
+                base_a += int(v) * self._stride(ax)
+        oa = []
+        for m in range(self._num_modes):
+            if m in modes:
+                continue
+            for ax in self._mode_axes(m):
+                oa.append((D, self._stride(ax), 0, self._stride(ax)))
+        self._gather(self._buf, None, out, oa, base=(base_a, 0, 0))
+        if self._shared:  # the old buffer belongs to a state object now
+            self._buf, self._scratch, self._shared = out, None, False
+        else:
+            self._buf, self._scratch = out, self._buf
+
+    def _renormalise(self):
+        self._own()
+        nrm = self._norm_device()
+        if float(nrm[0].item()) == 0:
+            raise ZeroDivisionError("Measurement has zero probability.")
+        L.call("b200_scale", _ptr(self._buf), self._buf.numel(), 1.0, 0.0, _ptr(nrm), 1 if self._pure else 0,
+               self._stream())
+
+    def measure_fock(self, modes, select=None):
+        if self._batched:
+            raise NotImplementedError("measure_fock on a batched b200fock circuit is not supported yet")
+        if select is not None and np.any(np.array(select) == None):  # noqa: E711
+            raise NotImplementedError("Post-selection lists must only contain numerical values.")
+        self._flush()
+        D = self._trunc
+
+        if select is not None:
+            if len(select) != len(modes):
+                raise ValueError(
+                    "When performing post-selection, the number of "
+                    "selected values (including None) must match the number of measured modes"
+                )
+            if not all(isinstance(s, int) or s is None for s in select):
+                raise TypeError("The post-select list elements either be integers or None")
+            measure = [i for i, s in zip(modes, select) if s is None]
+            selected = [i for i, s in zip(modes, select) if s is not None]
+            select_values = [s for s in select if s is not None]
+            # NB: like the reference, the distribution below would be taken from the state BEFORE the
+            # projection (circuit.py:632-635); with all-numeric `select` nothing is left to sample.
+            self._project_reset(selected, select_values)
+            self._renormalise()
+            self._touch(*selected)
+        else:
+            measure = list(modes)
+
+        if len(measure) > 0:
+            keep = sorted(measure)
+            dist = self.marginal_probs_device(keep)[0].cpu().numpy()
+            # steps 3-6 of SURVEY Appendix B, with numpy itself so the draw is bit-identical
+            dist = dist * ~np.isclose(dist, 0.0)
+            if sum(dist) != 1:
+                i = np.random.choice(list(range(len(dist))), p=dist / sum(dist))
+            else:
+                i = np.random.choice(list(range(len(dist))), p=dist)
+            digits = [i // D ** (len(measure) - 1 - m) % D for m in range(len(measure))]
+            permutation = np.argsort(measure)
+            outcome = [0] * len(measure)
+            for j in range(len(measure)):
+                outcome[permutation[j]] = int(digits[j])
+            self._project_reset(measure, outcome)
+            self._renormalise()
+            self._touch(*measure)
+
+        if select is not None:
+            outcome = copy.copy(select)
+        return np.array([outcome])
+
+
+    # ------------------------------------------------------------------ homodyne (circuit.py:713-801)
+    def measure_homodyne(self, phi, mode, select=None, **kwargs):
+        """Homodyne measurement.  The single-mode marginal (a D x D reduced density matrix
+        computed on the device) is sampled on the host grid exactly as the reference does; the
+        conditional state is obtained by applying |0><x_phi| with the dense gate kernel."""
+        import numbers
+
+        if self._batched:
+            raise NotImplementedError("measure_homodyne on a batched b200fock circuit is not supported yet")
+        self._flush()
+        D = self._trunc
+        w = 1 / self._hbar  # m omega / hbar
+        if select is not None:
+            if not isinstance(select, numbers.Number):
+                raise TypeError("Selected measurement result must be of numeric type.")
+            sample = float(select)
+        else:
+            rho = self.reduced_dm_device([mode])[0].cpu().numpy().reshape(D, D)
+            ph = np.exp(-1j * phi * np.arange(D))
+            rho = ph[:, None] * rho * ph.conj()[None, :]  # rotate to the measurement basis
+            q_mag = kwargs.get("max", 10)
+            num_bins = kwargs.get("num_bins", 100000)
+            q = np.linspace(-q_mag, q_mag, num_bins)
+            x = np.sqrt(w) * q
+            H = [np.ones_like(x), 2 * x]
+            for i in range(2, D):
+                H.append(2 * x * H[i - 1] - 2 * (i - 1) * H[i - 2])
+            scale = np.array([1 / np.sqrt(2.0 ** n * factorial(n)) for n in range(D)])
+            Hn = np.array(H[:D]) * scale[:, None]  # normalised Hermite functions without the Gaussian
+            pdf = np.einsum("nm,nq,mq->q", rho, Hn, Hn)
+            pdf = pdf * (w / np.pi) ** 0.5 * np.exp(-w * q ** 2) * (q[1] - q[0])
+            probs = pdf.real
+            probs /= np.sum(probs)
+            probs[np.abs(probs) < 1e-10] = 0
+            hist = np.random.multinomial(1, probs)
+            sample = q[list(hist).index(1)]
+
+        inf_sq = np.array([(-0.5) ** (n // 2) * np.sqrt(factorial(n)) / factorial(n // 2) if n % 2 == 0 else 0.0
+                           for n in range(D)], dtype=C128)
+        alpha = sample * np.sqrt(w / 2)
+        disp = self._gen1(L.GATE_DISPLACEMENT, float(np.abs(alpha)), float(np.angle(alpha)))[0].cpu().numpy()
+        eig = (np.exp(1j * phi * np.arange(D))[:, None] * disp) @ inf_sq
+        proj = np.zeros((D, D), dtype=C128)
+        proj[0, :] = eig.conj()
+        self._touch(mode)
+        self._apply_dense_now(self._upload_matrix(proj), mode)
+        self._own()
+        nrm = self._norm_device()
+        L.call("b200_scale", _ptr(self._buf), self._buf.numel(), 1.0, 0.0, _ptr(nrm), 1 if self._pure else 0,
+               self._stream())
+        return np.array([[sample]])
+
+
+# ---------------------------------------------------------------------- host-built single-mode kets
+def _coherent(r, phi, D):
+    alpha = r * np.exp(1j * phi)
+    return np.exp(-abs(alpha) ** 2 / 2) * np.array(
+        [alpha ** n / np.sqrt(factorial(n)) for n in range(D)], dtype=C128)
+
+
+def _squeezed(r, theta, D):
+    v = np.zeros(D, dtype=C128)
+    for n in range(0, D, 2):
+        m = n // 2
+        v[n] = (np.sqrt(factorial(2 * m)) / (2 ** m * factorial(m))) * (-np.exp(1j * theta) * np.tanh(r)) ** m
+    return np.sqrt(1 / np.cosh(r)) * v
+
+
+def _displaced_squeezed(r_d, phi_d, r_s, phi_s, D):
+    """fockbackend/ops.py:419-446 (Hermite-polynomial closed form)."""
+    from numpy.polynomial.hermite import hermval
+
+    if np.allclose(r_s, 0.0):
+        return _coherent(r_d, phi_d, D)
+    if np.allclose(r_d, 0.0):
+        return _squeezed(r_s, phi_s, D)
+    ph = np.exp(1j * phi_s)
+    ch, sh, th = np.cosh(r_s), np.sinh(r_s), np.tanh(r_s)
+    alpha = r_d * np.exp(1j * phi_d)
+    gamma = alpha * ch + np.conj(alpha) * ph * sh
+    harg = gamma / np.sqrt(ph * np.sinh(2 * r_s) + 1e-10)
+    N = np.exp(-0.5 * np.abs(alpha) ** 2 - 0.5 * np.conj(alpha) ** 2 * ph * th)
+    coeff = np.array([(0.5 * ph * th) ** (n / 2) / np.sqrt(factorial(n) * ch) for n in range(D)])
+    return N * np.array([hermval(harg, row) for row in np.diag(coeff)])

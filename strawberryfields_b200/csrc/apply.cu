@@ -1,0 +1,370 @@
+// Gate application kernels (K1-K7 in SURVEY.md section 2): one universal "blocked
+// arithmetic-progression contraction".
+//
+// Every gate on the path is block-diagonal over index sets that are arithmetic
+// progressions in memory:
+//   * dense one-mode gate on axis a:            one block of D members, step = stride(a)
+//   * BSgate / MZgate (i+j = k+l conserved):     blocks b = i+j, members (lo+m, b-lo-m),
+//                                                step = stride1 - stride2
+//   * S2gate, loss superoperator (i-j conserved): blocks b = i-j+D-1, members (lo+m, lo+m-d),
+//                                                step = stride1 + stride2
+// A "slice" fixes all other indices.  Work is cut into tasks of exactly D amplitudes per
+// slice (the middle block alone, every other block paired with its complement), so a
+// two-mode gate has the same shape as a one-mode gate: N/D tasks, each loading D
+// amplitudes into registers, multiplying by small dense matrices broadcast from shared
+// memory, and storing D amplitudes back in place.  Lanes of a warp run over consecutive
+// slices (the fastest remaining index), which makes every load/store a run of
+// consecutive 16-byte amplitudes whenever the inner stride allows.
+//
+// Replaces Circuit.apply_gate_BLAS (fockbackend/circuit.py:118-217),
+// Circuit.apply_twomode_gate + numba kernels (circuit.py:219-365) and, for the loss
+// channel, Circuit._apply_channel (circuit.py:65-87) of the reference.
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int MAX_TASKS = B200_MAX_CUTOFF;
+
+struct SubBlock {
+  int c;        // members (0 = unused)
+  int coef;     // offset of the c x c matrix in the packed table
+  int start_k;  // first member's index on axis 1
+  int start_l;  // first member's index on axis 2
+};
+struct TaskTable {
+  int ntasks;
+  int dl;  // per-member step on axis 2: -1 (SUM), +1 (DIFF), 0 (SINGLE)
+  SubBlock sub[MAX_TASKS][2];
+};
+
+struct Geometry {
+  // slice s (0 <= s < n_slices) -> element offset
+  //   (s / (mid*inner)) * outer_step + ((s / inner) % mid) * mid_step + (s % inner)
+  unsigned n_slices;
+  unsigned inner, mid;
+  long long outer_step, mid_step;
+  long long stride1, stride2;  // element strides of the gate axes (stride2 = 0 for SINGLE)
+  long long state_batch_stride;
+  long long coef_batch_stride;
+  int coef_count;  // packed entries to stage in shared memory
+  int conj;
+};
+
+template <int C>
+__device__ __forceinline__ void block_apply(cplx* __restrict__ p, long long step,
+                                            const cplx* __restrict__ M) {
+  cplx x[C];
+#pragma unroll
+  for (int j = 0; j < C; ++j) x[j] = p[j * step];
+#pragma unroll 2
+  for (int a = 0; a < C; ++a) {
+    cplx acc = make_double2(0.0, 0.0);
+#pragma unroll
+    for (int j = 0; j < C; ++j) cfma(acc, M[a * C + j], x[j]);
+    p[a * step] = acc;
+  }
+}
+
+// any block size (cutoffs above B200_MAX_FAST_CUTOFF): amplitudes staged in local memory
+__device__ __noinline__ void block_apply_dyn(int c, cplx* __restrict__ p, long long step,
+                                             const cplx* __restrict__ M) {
+  cplx x[B200_MAX_CUTOFF];
+  for (int j = 0; j < c; ++j) x[j] = p[j * step];
+  for (int a = 0; a < c; ++a) {
+    cplx acc = make_double2(0.0, 0.0);
+    for (int j = 0; j < c; ++j) cfma(acc, M[a * c + j], x[j]);
+    p[a * step] = acc;
+  }
+}
+
+__device__ __forceinline__ void block_dispatch(int c, cplx* p, long long step, const cplx* M) {
+  switch (c) {
+    case 1: block_apply<1>(p, step, M); break;
+    case 2: block_apply<2>(p, step, M); break;
+    case 3: block_apply<3>(p, step, M); break;
+    case 4: block_apply<4>(p, step, M); break;
+    case 5: block_apply<5>(p, step, M); break;
+    case 6: block_apply<6>(p, step, M); break;
+    case 7: block_apply<7>(p, step, M); break;
+    case 8: block_apply<8>(p, step, M); break;
+    case 9: block_apply<9>(p, step, M); break;
+    case 10: block_apply<10>(p, step, M); break;
+    case 11: block_apply<11>(p, step, M); break;
+    case 12: block_apply<12>(p, step, M); break;
+    case 13: block_apply<13>(p, step, M); break;
+    case 14: block_apply<14>(p, step, M); break;
+    case 15: block_apply<15>(p, step, M); break;
+    case 16: block_apply<16>(p, step, M); break;
+    default: block_apply_dyn(c, p, step, M); break;
+  }
+}
+
+constexpr int APPLY_THREADS = 256;
+
+// grid: (slice groups, 1, nbatch).  CTA = 8 warps; warp-task = (32 consecutive slices, task).
+// A CTA owns `groups_per_cta` slice groups x all tasks and its warps stride over them.
+__global__ void __launch_bounds__(APPLY_THREADS)
+k_apply_blocks(cplx* __restrict__ state, const cplx* __restrict__ coef, Geometry g, TaskTable tt,
+               int groups_per_cta) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* M = reinterpret_cast<cplx*>(smem_raw);
+  const int batch = blockIdx.z;
+  const cplx* cg = coef + (size_t)batch * g.coef_batch_stride;
+  for (int i = threadIdx.x; i < g.coef_count; i += APPLY_THREADS) {
+    cplx v = cg[i];
+    if (g.conj) v.y = -v.y;
+    M[i] = v;
+  }
+  __syncthreads();
+
+  cplx* base = state + (size_t)batch * g.state_batch_stride;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long step = g.stride1 + (long long)tt.dl * g.stride2;
+  const unsigned group0 = blockIdx.x * (unsigned)groups_per_cta;
+  const int n_wt = groups_per_cta * tt.ntasks;
+  for (int wt = warp; wt < n_wt; wt += APPLY_THREADS / 32) {
+    const int gi = wt / tt.ntasks, task = wt - gi * tt.ntasks;
+    const unsigned s = (group0 + gi) * 32u + lane;
+    if (s >= g.n_slices) continue;
+    const unsigned i_in = s % g.inner, rest = s / g.inner;
+    const unsigned i_mid = rest % g.mid, i_out = rest / g.mid;
+    cplx* ps = base + (long long)i_out * g.outer_step + (long long)i_mid * g.mid_step + i_in;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const SubBlock sb = tt.sub[task][h];
+      if (sb.c == 0) continue;
+      block_dispatch(sb.c, ps + sb.start_k * g.stride1 + sb.start_l * g.stride2, step, M + sb.coef);
+    }
+  }
+}
+
+// ---- diagonal gates ---------------------------------------------------------------------
+// state[e] *= tab[digit1(e)] or tab[digit1(e) * D + digit2(e)]
+__global__ void __launch_bounds__(256)
+k_apply_diag(cplx* __restrict__ state, long long total, int D, long long stride1, long long stride2,
+             const cplx* __restrict__ tab, int conj, long long state_batch_stride, long long tab_batch_stride) {
+  __shared__ cplx T[B200_MAX_CUTOFF * B200_MAX_CUTOFF > 1024 ? 1024 : B200_MAX_CUTOFF * B200_MAX_CUTOFF];
+  const int batch = blockIdx.z;
+  const int ntab = stride2 ? D * D : D;
+  const cplx* tg = tab + (size_t)batch * tab_batch_stride;
+  const bool in_smem = ntab <= 1024;
+  if (in_smem) {
+    for (int i = threadIdx.x; i < ntab; i += blockDim.x) {
+      cplx v = tg[i];
+      if (conj) v.y = -v.y;
+      T[i] = v;
+    }
+    __syncthreads();
+  }
+  cplx* base = state + (size_t)batch * state_batch_stride;
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += nthreads) {
+    int d1 = (int)((e / stride1) % D);
+    int idx = d1;
+    if (stride2) idx = d1 * D + (int)((e / stride2) % D);
+    cplx f;
+    if (in_smem) f = T[idx];
+    else {
+      f = tg[idx];
+      if (conj) f.y = -f.y;
+    }
+    base[e] = cmul(base[e], f);
+  }
+}
+
+struct MultiDiag {
+  int naxes;
+  int conj[B200_MAX_AXES];
+  long long stride[B200_MAX_AXES];
+};
+// state[e] *= prod_k tabs[k][digit_k(e)] -- every pending diagonal gate in one pass
+__global__ void __launch_bounds__(256)
+k_apply_diag_multi(cplx* __restrict__ state, long long total, int D, MultiDiag md,
+                   const cplx* __restrict__ tabs, long long state_batch_stride, long long tab_batch_stride) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* T = reinterpret_cast<cplx*>(smem_raw);
+  const int batch = blockIdx.z;
+  const cplx* tg = tabs + (size_t)batch * tab_batch_stride;
+  for (int i = threadIdx.x; i < md.naxes * D; i += blockDim.x) {
+    cplx v = tg[i];
+    if (md.conj[i / D]) v.y = -v.y;
+    T[i] = v;
+  }
+  __syncthreads();
+  cplx* base = state + (size_t)batch * state_batch_stride;
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += nthreads) {
+    cplx f = T[(int)((e / md.stride[0]) % D)];
+    for (int k = 1; k < md.naxes; ++k) f = cmul(f, T[k * D + (int)((e / md.stride[k]) % D)]);
+    base[e] = cmul(base[e], f);
+  }
+}
+
+__global__ void k_mul_tables(long long n, const cplx* __restrict__ a, const cplx* __restrict__ b, int conj_b,
+                             cplx* __restrict__ out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  cplx w = b[i];
+  if (conj_b) w.y = -w.y;
+  out[i] = cmul(a[i], w);
+}
+
+// ---- host side ------------------------------------------------------------------------------
+static void build_tasks(int rule, int D, TaskTable& tt) {
+  memset(&tt, 0, sizeof(tt));
+  if (rule == B200_RULE_SINGLE) {
+    tt.ntasks = 1;
+    tt.dl = 0;
+    tt.sub[0][0] = SubBlock{D, 0, 0, 0};
+    return;
+  }
+  tt.dl = (rule == B200_RULE_SUM) ? -1 : +1;
+  auto make = [&](int b) {
+    int lo = blk_lo(b, D);
+    SubBlock s;
+    s.c = blk_size(b, D);
+    s.coef = blk_off(b, D);
+    s.start_k = lo;
+    s.start_l = (rule == B200_RULE_SUM) ? (b - lo) : (lo - (b - (D - 1)));
+    return s;
+  };
+  // blocks sorted by size: lower half b (size b+1) and upper half 2D-2-b (same size);
+  // the i-th smallest is paired with the i-th largest so that every task holds D amplitudes.
+  int order[2 * B200_MAX_CUTOFF];
+  int n = 0;
+  for (int b = 0; b <= D - 2; ++b) {
+    order[n++] = b;
+    order[n++] = 2 * D - 2 - b;
+  }
+  int t = 0;
+  tt.sub[t++][0] = make(D - 1);  // the middle block, D members
+  for (int i = 0; i < n / 2; ++i) {
+    tt.sub[t][0] = make(order[n - 1 - i]);
+    tt.sub[t][1] = make(order[i]);
+    ++t;
+  }
+  tt.ntasks = t;
+}
+
+static int launch_blocks(cplx* state, const cplx* coef, Geometry& g, const TaskTable& tt, int nbatch,
+                         cudaStream_t st) {
+  size_t smem = (size_t)g.coef_count * sizeof(cplx);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k_apply_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail((int)e, "apply: shared memory opt-in failed: %s", cudaGetErrorString(e));
+  }
+  unsigned n_groups = (g.n_slices + 31u) / 32u;
+  // ~16 warp-tasks per CTA: two per warp, enough to amortise staging the gate table
+  int gpc = tt.ntasks >= 16 ? 1 : (16 + tt.ntasks - 1) / tt.ntasks;
+  unsigned n_cta = (n_groups + gpc - 1) / gpc;
+  dim3 grid(n_cta, 1, nbatch);
+  k_apply_blocks<<<grid, APPLY_THREADS, smem, st>>>(state, coef, g, tt, gpc);
+  return cuda_status("apply_blocks");
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200_apply_gate1(b200_c128* state_dev, int64_t outer, int D, int64_t inner, const b200_c128* U_dev,
+                     int conj, int nbatch, int64_t state_batch_stride, int64_t gate_batch_stride,
+                     void* stream) {
+  B200_CHECK_ARG(state_dev && U_dev, "apply_gate1: null pointer");
+  B200_CHECK_ARG(D >= 1 && D <= B200_MAX_CUTOFF, "apply_gate1: cutoff out of range");
+  B200_CHECK_ARG(outer >= 1 && inner >= 1 && nbatch >= 1, "apply_gate1: bad geometry");
+  B200_CHECK_ARG(outer * inner < (1ll << 32) && inner < (1ll << 32), "apply_gate1: too many slices for one launch");
+  Geometry g;
+  g.n_slices = (unsigned)(outer * inner);
+  g.inner = (unsigned)inner;
+  g.mid = 1;
+  g.outer_step = (long long)D * inner;
+  g.mid_step = 0;
+  g.stride1 = inner;
+  g.stride2 = 0;
+  g.state_batch_stride = state_batch_stride;
+  g.coef_batch_stride = gate_batch_stride;
+  g.coef_count = D * D;
+  g.conj = conj;
+  TaskTable tt;
+  build_tasks(B200_RULE_SINGLE, D, tt);
+  return launch_blocks((cplx*)state_dev, (const cplx*)U_dev, g, tt, nbatch, (cudaStream_t)stream);
+}
+
+int b200_apply_gate2(b200_c128* state_dev, int64_t total, int D, int64_t stride1, int64_t stride2, int rule,
+                     const b200_c128* packed_dev, int conj, int nbatch, int64_t state_batch_stride,
+                     int64_t gate_batch_stride, void* stream) {
+  B200_CHECK_ARG(state_dev && packed_dev, "apply_gate2: null pointer");
+  B200_CHECK_ARG(rule == B200_RULE_SUM || rule == B200_RULE_DIFF, "apply_gate2: bad rule");
+  B200_CHECK_ARG(D >= 1 && D <= B200_MAX_CUTOFF, "apply_gate2: cutoff out of range");
+  B200_CHECK_ARG(stride1 >= 1 && stride2 >= 1 && stride1 != stride2 && nbatch >= 1, "apply_gate2: bad strides");
+  int64_t hi = stride1 > stride2 ? stride1 : stride2, lo = stride1 > stride2 ? stride2 : stride1;
+  B200_CHECK_ARG(hi % ((int64_t)D * lo) == 0 && total % ((int64_t)D * hi) == 0, "apply_gate2: strides do not tile the state");
+  int64_t slices = total / ((int64_t)D * D);
+  B200_CHECK_ARG(slices < (1ll << 32) && lo < (1ll << 32), "apply_gate2: too many slices for one launch");
+  Geometry g;
+  g.n_slices = (unsigned)slices;
+  g.inner = (unsigned)lo;
+  g.mid = (unsigned)(hi / ((int64_t)D * lo));
+  g.outer_step = (long long)D * hi;
+  g.mid_step = (long long)D * lo;
+  g.stride1 = stride1;
+  g.stride2 = stride2;
+  g.state_batch_stride = state_batch_stride;
+  g.coef_batch_stride = gate_batch_stride;
+  g.coef_count = packed_size(D);
+  g.conj = conj;
+  TaskTable tt;
+  build_tasks(rule, D, tt);
+  return launch_blocks((cplx*)state_dev, (const cplx*)packed_dev, g, tt, nbatch, (cudaStream_t)stream);
+}
+
+int b200_apply_diag(b200_c128* state_dev, int64_t total, int D, int64_t stride1, int64_t stride2,
+                    const b200_c128* tab_dev, int conj, int nbatch, int64_t state_batch_stride,
+                    int64_t tab_batch_stride, void* stream) {
+  B200_CHECK_ARG(state_dev && tab_dev, "apply_diag: null pointer");
+  B200_CHECK_ARG(D >= 1 && D <= B200_MAX_CUTOFF && total >= 1 && stride1 >= 1 && stride2 >= 0 && nbatch >= 1,
+                 "apply_diag: bad geometry");
+  long long want = (total + 255) / 256;
+  unsigned blocks = (unsigned)(want < 148 * 16 ? want : 148 * 16);
+  dim3 grid(blocks, 1, nbatch);
+  k_apply_diag<<<grid, 256, 0, (cudaStream_t)stream>>>((cplx*)state_dev, total, D, stride1, stride2,
+                                                       (const cplx*)tab_dev, conj, state_batch_stride,
+                                                       tab_batch_stride);
+  return cuda_status("apply_diag");
+}
+
+int b200_apply_diag_multi(b200_c128* state_dev, int64_t total, int D, int naxes, const int64_t* strides,
+                          const int* conj_flags, const b200_c128* tabs_dev, int nbatch,
+                          int64_t state_batch_stride, int64_t tab_batch_stride, void* stream) {
+  B200_CHECK_ARG(state_dev && tabs_dev && strides && conj_flags, "apply_diag_multi: null pointer");
+  B200_CHECK_ARG(naxes >= 1 && naxes <= B200_MAX_AXES, "apply_diag_multi: bad axis count");
+  B200_CHECK_ARG(D >= 1 && D <= B200_MAX_CUTOFF && total >= 1 && nbatch >= 1, "apply_diag_multi: bad geometry");
+  MultiDiag md;
+  md.naxes = naxes;
+  for (int k = 0; k < naxes; ++k) {
+    B200_CHECK_ARG(strides[k] >= 1, "apply_diag_multi: bad stride");
+    md.stride[k] = strides[k];
+    md.conj[k] = conj_flags[k];
+  }
+  long long want = (total + 255) / 256;
+  unsigned blocks = (unsigned)(want < 148 * 16 ? want : 148 * 16);
+  dim3 grid(blocks, 1, nbatch);
+  size_t smem = (size_t)naxes * D * sizeof(cplx);
+  k_apply_diag_multi<<<grid, 256, smem, (cudaStream_t)stream>>>((cplx*)state_dev, total, D, md,
+                                                                (const cplx*)tabs_dev, state_batch_stride,
+                                                                tab_batch_stride);
+  return cuda_status("apply_diag_multi");
+}
+
+int b200_mul_tables(int64_t n, const b200_c128* a_dev, const b200_c128* b_dev, int conj_b, b200_c128* out_dev,
+                    void* stream) {
+  B200_CHECK_ARG(n >= 1 && a_dev && b_dev && out_dev, "mul_tables: bad args");
+  k_mul_tables<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(n, (const cplx*)a_dev,
+                                                                            (const cplx*)b_dev, conj_b,
+                                                                            (cplx*)out_dev);
+  return cuda_status("mul_tables");
+}
+
+}  // extern "C"

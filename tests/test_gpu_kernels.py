@@ -1,0 +1,258 @@
+"""Kernel-level parity through the C ABI (libb200fock.so) against the oracle, on the GPU.
+
+Tolerance 1e-12 absolute (complex128), as stated in BASELINE.json's north_star.  Covers
+every cutoff the register-blocked kernels are instantiated for, the local-memory path
+above B200_MAX_FAST_CUTOFF, every axis position (first / middle / last mode), both
+selection rules, ragged slice counts and the batched layouts."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import gates as og
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from strawberryfields_b200 import lib as L
+
+    L.load()
+    return L
+
+
+@pytest.fixture(scope="module")
+def torch_mod():
+    import torch
+
+    return torch
+
+
+def _dev(torch, arr):
+    return torch.from_numpy(np.ascontiguousarray(arr)).cuda()
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def _rand(rs, *shape):
+    return rs.randn(*shape) + 1j * rs.randn(*shape)
+
+
+# ---------------------------------------------------------------------------- gate tables
+@pytest.mark.parametrize("D", [1, 2, 3, 5, 7, 10, 13, 16, 20])
+def test_gen_gate1(lib, torch_mod, D):
+    torch = torch_mod
+    for kind, fn, (a, b) in ((lib.GATE_DISPLACEMENT, og.displacement, (0.7, 1.3)),
+                             (lib.GATE_SQUEEZE, og.squeezing, (0.45, -0.8))):
+        out = torch.empty(D * D, dtype=torch.complex128, device="cuda")
+        lib.call("b200_gen_gate1", kind, D, 1, a, b, None, _p(out), None)
+        assert np.abs(out.cpu().numpy().reshape(D, D) - fn(a, b, D)).max() < TOL
+
+
+def test_gen_gate1_batched(lib, torch_mod):
+    torch = torch_mod
+    D, B = 9, 5
+    rs = np.random.RandomState(1)
+    params = np.stack([rs.uniform(0, 0.6, B), rs.uniform(-3, 3, B)])
+    pd = _dev(torch, params)
+    out = torch.empty(B * D * D, dtype=torch.complex128, device="cuda")
+    lib.call("b200_gen_gate1", lib.GATE_SQUEEZE, D, B, 0.0, 0.0, _p(pd), _p(out), None)
+    got = out.cpu().numpy().reshape(B, D, D)
+    for b in range(B):
+        assert np.abs(got[b] - og.squeezing(params[0, b], params[1, b], D)).max() < TOL
+
+
+@pytest.mark.parametrize("D", [1, 2, 3, 4, 7, 10, 12, 16])
+def test_gen_gate2_and_unpack(lib, torch_mod, D):
+    torch = torch_mod
+    P = lib.packed_size(D)
+    cases = [
+        (lib.GATE_BEAMSPLITTER, lib.RULE_SUM, og.beamsplitter, (0.6, 0.9)),
+        (lib.GATE_BEAMSPLITTER, lib.RULE_SUM, og.beamsplitter, (-1.2, 0.0)),
+        (lib.GATE_MZ, lib.RULE_SUM, og.mzgate, (0.3, 1.2)),
+        (lib.GATE_S2, lib.RULE_DIFF, og.two_mode_squeeze, (0.35, 0.4)),
+    ]
+    for kind, rule, fn, (a, b) in cases:
+        packed = torch.empty(P, dtype=torch.complex128, device="cuda")
+        dense = torch.empty(D ** 4, dtype=torch.complex128, device="cuda")
+        lib.call("b200_gen_gate2", kind, D, 1, a, b, None, _p(packed), None)
+        lib.call("b200_unpack_gate2", rule, D, _p(packed), _p(dense), None)
+        assert np.abs(dense.cpu().numpy().reshape((D,) * 4) - fn(a, b, D)).max() < TOL
+
+
+@pytest.mark.parametrize("T", [0.0, 0.37, 0.9, 1.0])
+def test_gen_loss_superoperator(lib, torch_mod, T):
+    torch = torch_mod
+    D = 8
+    P = lib.packed_size(D)
+    packed = torch.empty(P, dtype=torch.complex128, device="cuda")
+    dense = torch.empty(D ** 4, dtype=torch.complex128, device="cuda")
+    lib.call("b200_gen_gate2", lib.CHANNEL_LOSS, D, 1, T, 0.0, None, _p(packed), None)
+    lib.call("b200_unpack_gate2", lib.RULE_DIFF, D, _p(packed), _p(dense), None)
+    S = np.zeros((D,) * 4, dtype=complex)
+    for E in og.loss_kraus(T, D):  # fockbackend/ops.py:471-490
+        S += np.einsum("ab,cd->abcd", E, E.conj())
+    assert np.abs(dense.cpu().numpy().reshape((D,) * 4) - S).max() < TOL
+
+
+def test_gen_diag(lib, torch_mod):
+    torch = torch_mod
+    D = 11
+    n = np.arange(D)
+    for kind, p, want in ((lib.DIAG_ROTATION, 0.77, np.exp(1j * 0.77 * n)),
+                          (lib.DIAG_KERR, -0.31, np.exp(-1j * 0.31 * n ** 2)),
+                          (lib.DIAG_CROSS_KERR, 0.2, np.exp(1j * 0.2 * np.multiply.outer(n, n)).reshape(-1))):
+        out = torch.empty(want.size, dtype=torch.complex128, device="cuda")
+        lib.call("b200_gen_diag", kind, D, 1, p, None, _p(out), None)
+        assert np.abs(out.cpu().numpy() - want).max() < TOL
+
+
+# ---------------------------------------------------------------------------- gate application
+@pytest.mark.parametrize("D", [2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 21])
+def test_apply_gate1_every_axis(lib, torch_mod, D):
+    torch = torch_mod
+    rs = np.random.RandomState(D)
+    n = 4 if D <= 8 else 3
+    psi = _rand(rs, *([D] * n))
+    U = _rand(rs, D, D)
+    for axis in range(n):
+        for conj in (0, 1):
+            st = _dev(torch, psi.reshape(-1))
+            lib.call("b200_apply_gate1", _p(st), D ** axis, D, D ** (n - 1 - axis), _p(_dev(torch, U)), conj,
+                     1, D ** n, 0, None)
+            want = np.moveaxis(np.tensordot(U.conj() if conj else U, psi, axes=(1, axis)), 0, axis)
+            assert np.abs(st.cpu().numpy().reshape(psi.shape) - want).max() < 1e-11 * max(1, D)
+
+
+def test_apply_gate1_ragged_and_batched(lib, torch_mod):
+    torch = torch_mod
+    rs = np.random.RandomState(5)
+    D, B = 7, 3
+    outer, inner = 13, 5  # neither a multiple of the warp size
+    psi = _rand(rs, B, outer, D, inner)
+    U = _rand(rs, B, D, D)
+    st = _dev(torch, psi.reshape(-1))
+    lib.call("b200_apply_gate1", _p(st), outer, D, inner, _p(_dev(torch, U)), 0, B, outer * D * inner, D * D, None)
+    want = np.einsum("bxy,boyi->boxi", U, psi)
+    assert np.abs(st.cpu().numpy().reshape(psi.shape) - want).max() < TOL * 10
+
+
+@pytest.mark.parametrize("D", [2, 3, 5, 7, 10, 12, 16, 18])
+@pytest.mark.parametrize("rule", ["sum", "diff"])
+def test_apply_gate2_every_ordered_pair(lib, torch_mod, D, rule):
+    torch = torch_mod
+    rs = np.random.RandomState(100 + D)
+    n = 4 if D <= 7 else 3
+    psi = _rand(rs, *([D] * n))
+    if rule == "sum":
+        T, kind, rl = og.beamsplitter(0.7, 0.4, D), lib.GATE_BEAMSPLITTER, lib.RULE_SUM
+        args = (0.7, 0.4)
+    else:
+        T, kind, rl = og.two_mode_squeeze(0.3, 1.1, D), lib.GATE_S2, lib.RULE_DIFF
+        args = (0.3, 1.1)
+    packed = torch.empty(lib.packed_size(D), dtype=torch.complex128, device="cuda")
+    lib.call("b200_gen_gate2", kind, D, 1, args[0], args[1], None, _p(packed), None)
+    for a in range(n):
+        for b in range(n):
+            if a == b:
+                continue
+            for conj in (0, 1):
+                st = _dev(torch, psi.reshape(-1))
+                lib.call("b200_apply_gate2", _p(st), D ** n, D, D ** (n - 1 - a), D ** (n - 1 - b), rl,
+                         _p(packed), conj, 1, D ** n, 0, None)
+                Tc = T.conj() if conj else T
+                want = np.moveaxis(np.tensordot(Tc, psi, axes=([1, 3], [a, b])), [0, 1], [a, b])
+                assert np.abs(st.cpu().numpy().reshape(psi.shape) - want).max() < 1e-11
+
+
+def test_apply_gate2_batched_gate_tables(lib, torch_mod):
+    torch = torch_mod
+    rs = np.random.RandomState(9)
+    D, B, n = 6, 4, 3
+    psi = _rand(rs, B, *([D] * n))
+    params = np.stack([rs.uniform(0, 1.5, B), rs.uniform(0, 6, B)])
+    P = lib.packed_size(D)
+    packed = torch.empty(B * P, dtype=torch.complex128, device="cuda")
+    lib.call("b200_gen_gate2", lib.GATE_BEAMSPLITTER, D, B, 0.0, 0.0, _p(_dev(torch, params)), _p(packed), None)
+    st = _dev(torch, psi.reshape(-1))
+    lib.call("b200_apply_gate2", _p(st), D ** n, D, D ** 0, D ** 2, lib.RULE_SUM, _p(packed), 0, B, D ** n, P, None)
+    got = st.cpu().numpy().reshape(psi.shape)
+    for b in range(B):
+        T = og.beamsplitter(params[0, b], params[1, b], D)
+        want = np.moveaxis(np.tensordot(T, psi[b], axes=([1, 3], [2, 0])), [0, 1], [2, 0])
+        assert np.abs(got[b] - want).max() < TOL * 10
+
+
+def test_apply_diag_and_multi(lib, torch_mod):
+    torch = torch_mod
+    rs = np.random.RandomState(3)
+    D, n = 6, 4
+    psi = _rand(rs, *([D] * n))
+    t1 = np.exp(1j * rs.uniform(0, 6, D))
+    t2 = np.exp(1j * rs.uniform(0, 6, (D, D)))
+    st = _dev(torch, psi.reshape(-1))
+    lib.call("b200_apply_diag", _p(st), D ** n, D, D ** 2, 0, _p(_dev(torch, t1)), 0, 1, D ** n, 0, None)
+    assert np.abs(st.cpu().numpy().reshape(psi.shape) - psi * t1[None, :, None, None]).max() < TOL
+    st = _dev(torch, psi.reshape(-1))
+    lib.call("b200_apply_diag", _p(st), D ** n, D, D ** 0, D ** 3, _p(_dev(torch, t2.reshape(-1))), 1, 1, D ** n, 0, None)
+    want = psi * t2.conj().T[:, None, None, :]
+    assert np.abs(st.cpu().numpy().reshape(psi.shape) - want).max() < TOL
+    tabs = np.exp(1j * rs.uniform(0, 6, (3, D)))
+    st = _dev(torch, psi.reshape(-1))
+    strides = (C.c_int64 * 3)(D ** 3, D ** 1, D ** 0)
+    conjs = (C.c_int * 3)(0, 1, 0)
+    lib.call("b200_apply_diag_multi", _p(st), D ** n, D, 3, strides, conjs, _p(_dev(torch, tabs.reshape(-1))), 1,
+             D ** n, 0, None)
+    want = psi * tabs[0][:, None, None, None] * tabs[1].conj()[None, None, :, None] * tabs[2][None, None, None, :]
+    assert np.abs(st.cpu().numpy().reshape(psi.shape) - want).max() < TOL
+
+
+# ---------------------------------------------------------------------------- reductions
+def test_norm_abs2_scale(lib, torch_mod):
+    torch = torch_mod
+    rs = np.random.RandomState(4)
+    n = 1_234_567
+    psi = _rand(rs, n)
+    st = _dev(torch, psi)
+    out = torch.zeros(1, dtype=torch.float64, device="cuda")
+    part = torch.zeros(4096, dtype=torch.float64, device="cuda")
+    lib.call("b200_norm2", _p(st), n, _p(out), _p(part), None)
+    assert abs(out.item() - np.vdot(psi, psi).real) < 1e-9 * n ** 0.5
+    pr = torch.empty(n, dtype=torch.float64, device="cuda")
+    lib.call("b200_abs2", _p(st), _p(pr), n, None)
+    assert np.abs(pr.cpu().numpy() - np.abs(psi) ** 2).max() < TOL
+    lib.call("b200_scale", _p(st), n, 1.0, 0.0, _p(out), 1, None)
+    assert np.abs(st.cpu().numpy() - psi / np.linalg.norm(psi)).max() < TOL
+
+
+def test_gather_reduce_split_reduction(lib, torch_mod):
+    """single-mode marginal of a large pure state: few outputs, long reduction (split path)"""
+    torch = torch_mod
+    rs = np.random.RandomState(8)
+    D, n = 10, 5
+    psi = _rand(rs, *([D] * n))
+    st = _dev(torch, psi.reshape(-1))
+    d = lib.GatherDesc()
+    d.n_out_axes, d.n_red_axes = 1, 2
+    d.out_ext[0], d.out_sa[0], d.out_sb[0], d.out_sc[0] = D, D ** 2, D ** 2, 1
+    d.red_ext[0], d.red_ta[0], d.red_tb[0] = D ** 2, D ** 3, D ** 3
+    d.red_ext[1], d.red_ta[1], d.red_tb[1] = D ** 2, 1, 1
+    out = torch.zeros(D, dtype=torch.float64, device="cuda")
+    part = torch.zeros(D * 64, dtype=torch.complex128, device="cuda")
+    lib.call("b200_gather_reduce", C.byref(d), _p(st), _p(st), _p(out), lib.FLAG_CONJ_B | lib.FLAG_REAL_OUT,
+             _p(part), None)
+    want = (np.abs(psi) ** 2).sum(axis=(0, 1, 3, 4))
+    assert np.abs(out.cpu().numpy() - want).max() < 1e-9
+
+
+def test_bad_arguments_fail_loudly(lib, torch_mod):
+    torch = torch_mod
+    st = torch.zeros(16, dtype=torch.complex128, device="cuda")
+    with pytest.raises(lib.B200Error):
+        lib.call("b200_apply_gate1", _p(st), 1, 200, 1, _p(st), 0, 1, 16, 0, None)
+    with pytest.raises(lib.B200Error):
+        lib.call("b200_apply_gate2", _p(st), 16, 2, 3, 1, lib.RULE_SUM, _p(st), 0, 1, 16, 0, None)
