@@ -132,6 +132,36 @@ int b200_apply_diag_multi(b200_c128* state_dev, int64_t total, int D, int naxes,
                           const b200_c128* tabs_dev, int nbatch, int64_t state_batch_stride,
                           int64_t tab_batch_stride, void* stream);
 
+/* ---- tile pass: several gates per HBM round trip ---------------------------------------
+ * A tile is the D x D x D sub-tensor spanned by two axes of element strides
+ * stride0 > stride1 (> 1) and the innermost axis (stride 1), every other index fixed.
+ * The kernel stages tiles in shared memory, applies `nops` operators IN ORDER to tile
+ * axes 0 (stride0), 1 (stride1), 2 (innermost), and writes the tiles back with tile axis
+ * k placed at tile position out_perm[k] (identity = {0,1,2}); the permutation lets the
+ * caller rotate which logical mode is innermost at no extra cost.
+ *   kind B200_RULE_SINGLE: dense D x D table on axis1
+ *   kind B200_RULE_SUM / B200_RULE_DIFF: block-packed table on (axis1, axis2)
+ *   kind B200_TILE_DIAG: table [D] on axis1
+ * conj != 0 applies the complex-conjugated table (bra side of a mixed state).
+ * coef_dev: [nbatch][coef_count] arena; each op names its own range (coef_offset).
+ * Cutoffs 2..B200_MAX_FAST_CUTOFF; fails with B200_EUNSUPPORTED when the tiles plus the
+ * operators' tables exceed shared memory (b200_tile_smem_bytes tells in advance).      */
+#define B200_TILE_DIAG 3
+#define B200_TILE_MAX_OPS 16
+typedef struct {
+  int kind;
+  int axis1, axis2;
+  int conj;
+  int64_t coef_offset;
+} b200_tile_op;
+int b200_tile_groups(int D);                          /* tiles staged per CTA */
+int64_t b200_tile_smem_bytes(int D, int64_t coef_count);
+int b200_apply_tile_pass(b200_c128* state_dev, int64_t total, int D, int64_t stride0,
+                         int64_t stride1, const b200_tile_op* ops, int nops,
+                         const int* out_perm, const b200_c128* coef_dev, int64_t coef_count,
+                         int nbatch, int64_t state_batch_stride, int64_t coef_batch_stride,
+                         void* stream);
+
 /* ---- strided gather / product / reduce (state preparation, partial traces, marginals,
  *      reduced density matrices; replaces the einsum helpers fockbackend/ops.py:110-198,
  *      circuit.py:393-473, backend.py:219-259, states.py:580-642)

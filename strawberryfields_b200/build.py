@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200fock.so")
-SOURCES = ["api.cu", "gates_gen.cu", "apply.cu", "generic.cu"]
+SOURCES = ["api.cu", "gates_gen.cu", "apply.cu", "tile.cu", "generic.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -32,7 +32,7 @@ def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = sources() + [os.path.join(CSRC, "common.cuh"),
+    deps = sources() + [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "blocks.cuh"),
                         os.path.join(os.path.dirname(HERE), "include", "b200fock.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 

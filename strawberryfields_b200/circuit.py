@@ -32,6 +32,7 @@ import numpy as np
 import torch
 
 from . import lib as L
+from . import scheduler as S
 
 C128 = np.complex128
 _HBAR = 2  # circuit.py:61
@@ -83,7 +84,7 @@ class DeviceCircuit:
         if self._B < 1:
             raise ValueError("batch_size must be a positive integer")
         self._strict = bool(strict_purity)
-        self._fuse = bool(fuse)
+        self._fuse = "fold" if fuse == "fold" else bool(fuse)
         self._scratch = None
         self._part = None
         self._norm_out = torch.zeros(2, dtype=torch.float64, device=self.device)
@@ -103,9 +104,38 @@ class DeviceCircuit:
         """elements per batch entry"""
         return self._trunc ** self._axes()
 
-    def _stride(self, axis, naxes=None):
-        naxes = self._axes() if naxes is None else naxes
-        return self._trunc ** (naxes - 1 - axis)
+    def _stride(self, axis):
+        """element stride of (virtual) tensor axis ``axis`` in the current physical layout"""
+        return self._trunc ** (len(self._pos) - 1 - self._pos[axis])
+
+    def _canon_stride(self, axis):
+        return self._trunc ** (self._axes() - 1 - axis)
+
+    def _set_identity_layout(self):
+        """physical position p holds virtual axis _phys[p]; _pos is the inverse map.  Tile passes
+        permute axes (scheduler.py); everything that reads the state goes through _stride()."""
+        self._phys = list(range(self._axes()))
+        self._pos = list(range(self._axes()))
+
+    def _is_canonical(self):
+        return all(p == v for p, v in enumerate(self._phys))
+
+    def _canonicalize(self):
+        """Restore the canonical axis order (one out-of-place strided copy)."""
+        if self._is_canonical():
+            return
+        D, B = self._trunc, self._B
+        per = self._size()
+        out = self._get_scratch(self._buf.numel())
+        oa = [(B, per, 0, per)] if B > 1 else []
+        for v in range(self._axes()):
+            oa.append((D, self._stride(v), 0, self._canon_stride(v)))
+        self._gather(self._buf, None, out, oa)
+        if self._shared:
+            self._buf, self._scratch, self._shared = out, None, False
+        else:
+            self._buf, self._scratch = out, self._buf
+        self._set_identity_layout()
 
     def _new(self, n):
         return torch.empty(int(n), dtype=torch.complex128, device=self.device)
@@ -135,6 +165,7 @@ class DeviceCircuit:
         snap = object.__new__(DeviceCircuit)
         snap.__dict__.update(self.__dict__)
         snap._pending = {}
+        snap._opq = []
         snap._untouched = set()
         snap._scratch = None
         snap._part = None
@@ -157,11 +188,14 @@ class DeviceCircuit:
         obj._part = None
         obj._norm_part = torch.zeros(4096, dtype=torch.float64, device=like.device)
         obj._shared = False
+        obj._opq = []
+        obj._set_identity_layout()
         return obj
 
     def permute_modes(self, perm):
         """New mode p <- old mode perm[p] (both tensor axes of a mode move together)."""
         self._flush()
+        self._canonicalize()
         D, B, n = self._trunc, self._B, self._num_modes
         per = self._size()
         out = self._new(self._buf.numel())
@@ -200,6 +234,8 @@ class DeviceCircuit:
         self._buf = self._new(self._B * per)
         self._vacuum(self._buf, per)
         self._pending = {}
+        self._opq = []
+        self._set_identity_layout()
         self._untouched = set(range(self._num_modes))
 
     # ------------------------------------------------------------------ gate tables
@@ -279,7 +315,8 @@ class DeviceCircuit:
         D, B = self._trunc, self._B
         naxes = self._axes()
         nb = U.shape[0]
-        self._pass("gate1/axis%d" % (naxes - 1 - axis), "b200_apply_gate1", _ptr(self._buf), D ** axis, D, D ** (naxes - 1 - axis), _ptr(U),
+        pos = self._pos[axis]
+        self._pass("gate1/axis%d" % (naxes - 1 - pos), "b200_apply_gate1", _ptr(self._buf), D ** pos, D, D ** (naxes - 1 - pos), _ptr(U),
                int(conj), B, self._size(), D * D if nb > 1 else 0, self._stream())
 
     def _k_gate2(self, G, rule, ax1, ax2, conj):
@@ -287,7 +324,8 @@ class DeviceCircuit:
         D, B = self._trunc, self._B
         nb = G.shape[0]
         naxes = self._axes()
-        self._pass("gate2/rule%d/axes%d,%d" % (rule, naxes - 1 - ax1, naxes - 1 - ax2), "b200_apply_gate2",
+        self._pass("gate2/rule%d/axes%d,%d" % (rule, naxes - 1 - self._pos[ax1], naxes - 1 - self._pos[ax2]),
+                   "b200_apply_gate2",
                    _ptr(self._buf), self._size(), D, self._stride(ax1), self._stride(ax2),
                rule, _ptr(G), int(conj), B, self._size(), G.shape[1] if nb > 1 else 0, self._stream())
 
@@ -333,6 +371,94 @@ class DeviceCircuit:
         else:
             self._k_gate2(G, rule, 2 * m1, 2 * m2, 0)
             self._k_gate2(G, rule, 2 * m1 + 1, 2 * m2 + 1, 1)
+
+    # ------------------------------------------------------------------ tile queue
+    def _tile_mode(self):
+        """Tile passes need >= 3 tensor axes, a cutoff the tile kernel is instantiated for, and
+        fuse=True (fuse="fold" keeps the one-pass-per-gate path with diagonal folding only)."""
+        return (self._fuse is True and 2 <= self._trunc <= L.MAX_FAST_CUTOFF and self._axes() >= 3)
+
+    def _emit_dense(self, U, mode):
+        """A dense single-mode operator leaves the fold stage: queue it (tile mode) or apply it."""
+        if not self._tile_mode():
+            self._apply_dense_now(U, mode)
+            return
+        sz = self._trunc ** 2
+        if self._pure:
+            self._opq.append(S.Op(S.KIND_SINGLE, (mode,), U, 0, sz))
+        else:
+            self._opq.append(S.Op(S.KIND_SINGLE, (2 * mode,), U, 0, sz))
+            self._opq.append(S.Op(S.KIND_SINGLE, (2 * mode + 1,), U, 1, sz))
+        self._queue_limit()
+
+    def _emit_diags(self, items):
+        if not self._tile_mode():
+            self._k_diag_multi(items)
+            return
+        for d, mode in items:
+            if self._pure:
+                self._opq.append(S.Op(S.KIND_DIAG, (mode,), d, 0, self._trunc, 0.2))
+            else:
+                self._opq.append(S.Op(S.KIND_DIAG, (2 * mode,), d, 0, self._trunc, 0.2))
+                self._opq.append(S.Op(S.KIND_DIAG, (2 * mode + 1,), d, 1, self._trunc, 0.2))
+        self._queue_limit()
+
+    def _emit_pair(self, G, rule, m1, m2):
+        if not self._tile_mode():
+            self._apply_pair_now(G, rule, m1, m2)
+            return
+        sz = L.packed_size(self._trunc)
+        if self._pure:
+            self._opq.append(S.Op(rule, (m1, m2), G, 0, sz))
+        else:
+            self._opq.append(S.Op(rule, (2 * m1, 2 * m2), G, 0, sz))
+            self._opq.append(S.Op(rule, (2 * m1 + 1, 2 * m2 + 1), G, 1, sz))
+        self._queue_limit()
+
+    def _queue_limit(self):
+        if len(self._opq) >= 96:  # bounds table memory and scheduling time on very long programs
+            self._run_queue()
+
+    def _run_queue(self):
+        """Schedule the queued operators into tile passes (scheduler.py) and launch them."""
+        if not self._opq:
+            return
+        ops, self._opq = self._opq, []
+        self._own()
+        D = self._trunc
+        tile_bytes = L.tile_smem_bytes(D, 0)
+        budget = (110 * 1024 - tile_bytes) // 16
+        if budget < L.packed_size(D):
+            budget = (L.SMEM_LIMIT - tile_bytes) // 16
+        passes, phys = S.plan(ops, self._phys, L.TILE_MAX_OPS, budget)
+        for p in passes:
+            self._launch_tile_pass(p)
+        self._phys = list(phys)
+        pos = [0] * len(phys)
+        for i, v in enumerate(phys):
+            pos[v] = i
+        self._pos = pos
+
+    def _launch_tile_pass(self, p):
+        D, B, A = self._trunc, self._B, self._axes()
+        nb = max([op.table.shape[0] for op, _ in p.ops] + [1])
+        tops = (L.TileOp * max(len(p.ops), 1))()
+        parts, off = [], 0
+        for i, (op, tax) in enumerate(p.ops):
+            tops[i].kind = op.kind
+            tops[i].axis1 = tax[0]
+            tops[i].axis2 = tax[1] if len(tax) > 1 else 0
+            tops[i].conj = int(op.conj)
+            tops[i].coef_offset = off
+            parts.append(self._expand(op.table.reshape(op.table.shape[0], -1), nb))
+            off += op.coef_size
+        coef = torch.cat(parts, dim=1).contiguous() if parts else None
+        perm = (C.c_int * 3)(*p.out_perm)
+        stride0 = D ** (A - 1 - p.positions[0])
+        stride1 = D ** (A - 1 - p.positions[1])
+        self._pass("tile/%dops" % len(p.ops), "b200_apply_tile_pass", _ptr(self._buf), self._size(), D, stride0,
+                   stride1, tops, len(p.ops), perm, _ptr(coef), off, B, self._size(), off if nb > 1 else 0,
+                   self._stream())
 
     # ------------------------------------------------------------------ lazy queue
     def _touch(self, *modes):
@@ -385,19 +511,22 @@ class DeviceCircuit:
             self._pending[mode] = ("dense", P)
 
     def _flush(self, modes=None):
-        """Apply pending single-mode operators of ``modes`` (default: all)."""
-        if not self._pending:
-            return
-        keys = sorted(self._pending) if modes is None else [m for m in modes if m in self._pending]
-        diags = []
-        for m in keys:
-            kind, tab = self._pending.pop(m)
-            if kind == "dense":
-                self._apply_dense_now(tab, m)
-            else:
-                diags.append((tab, m))
-        if diags:
-            self._k_diag_multi(diags)
+        """Move the pending single-mode operators of ``modes`` (default: all) out of the fold
+        stage.  A full flush (``modes is None``) also runs every queued tile pass, after which
+        the device buffer holds the up-to-date state."""
+        if self._pending:
+            keys = sorted(self._pending) if modes is None else [m for m in modes if m in self._pending]
+            diags = []
+            for m in keys:
+                kind, tab = self._pending.pop(m)
+                if kind == "dense":
+                    self._emit_dense(tab, m)
+                else:
+                    diags.append((tab, m))
+            if diags:
+                self._emit_diags(diags)
+        if modes is None:
+            self._run_queue()
 
     def _pair_gate(self, G, rule, m1, m2):
         """Two-mode gate: pending diagonals on its modes are folded into the table,
@@ -419,7 +548,7 @@ class DeviceCircuit:
             p1 = self._expand(pre[0], nb) if pre[0] is not None else None
             p2 = self._expand(pre[1], nb) if pre[1] is not None else None
             L.call("b200_fold_diag_gate2", rule, D, nb, _ptr(G), _ptr(p1), _ptr(p2), None, None, self._stream())
-        self._apply_pair_now(G, rule, m1, m2)
+        self._emit_pair(G, rule, m1, m2)
 
     # ------------------------------------------------------------------ named gates (circuit.py:537-598)
     def phase_shift(self, theta, mode):
@@ -461,6 +590,7 @@ class DeviceCircuit:
         # diagonal in both modes: commutes with pending diagonals, not with pending dense gates
         self._touch(mode1, mode2)
         self._flush([m for m in (mode1, mode2) if self._pending.get(m, ("", 0))[0] == "dense"])
+        self._run_queue()  # a two-axis diagonal is not a tile operator: apply it to the current state
         tab = self._gen_diag(L.DIAG_CROSS_KERR, kappa)
         if self._pure:
             self._k_diag_pair(tab, mode1, mode2, 0)
@@ -474,7 +604,11 @@ class DeviceCircuit:
         self._touch(mode)
         self._to_mixed()
         G = self._gen2(L.CHANNEL_LOSS, T)
-        self._k_gate2(G, L.RULE_DIFF, 2 * mode, 2 * mode + 1, 0)
+        if self._tile_mode():
+            self._opq.append(S.Op(S.KIND_DIFF, (2 * mode, 2 * mode + 1), G, 0, L.packed_size(self._trunc)))
+            self._queue_limit()
+        else:
+            self._k_gate2(G, L.RULE_DIFF, 2 * mode, 2 * mode + 1, 0)
 
     # ------------------------------------------------------------------ strided gather wrapper
     def _gather(self, A, B, Cout, out_axes, red_axes=(), flags=0, base=(0, 0, 0)):
@@ -521,7 +655,7 @@ class DeviceCircuit:
         new = self._new(B * per_m)
         axes = [(B, per_p, per_p, per_m)] if B > 1 else []
         for i in range(n):
-            st = D ** (n - 1 - i)
+            st = self._stride(i)
             axes.append((D, st, 0, D ** (2 * n - 1 - 2 * i)))
             axes.append((D, 0, st, D ** (2 * n - 2 - 2 * i)))
         self._gather(self._buf, self._buf, new, axes, flags=L.FLAG_CONJ_B)
@@ -529,6 +663,7 @@ class DeviceCircuit:
         self._shared = False
         self._scratch = None
         self._pure = False
+        self._set_identity_layout()
 
     # ------------------------------------------------------------------ norm (circuit.py:367-371)
     def _norm_device(self):
@@ -555,6 +690,7 @@ class DeviceCircuit:
     # ------------------------------------------------------------------ modes (circuit.py:373-391)
     def alloc(self, n=1):
         self._flush()
+        self._canonicalize()
         D, B = self._trunc, self._B
         k = self._axes()
         add = n if self._pure else 2 * n
@@ -570,6 +706,7 @@ class DeviceCircuit:
         for m in range(self._num_modes, self._num_modes + n):
             self._untouched.add(m)
         self._num_modes += n
+        self._set_identity_layout()
 
     def dealloc(self, modes):
         self._to_mixed()
@@ -579,6 +716,7 @@ class DeviceCircuit:
         self._shared = False
         self._scratch = None
         self._num_modes = len(keep)
+        self._set_identity_layout()
         self._untouched = set()
         self._pending = {}
 
@@ -604,6 +742,7 @@ class DeviceCircuit:
         if self._batched:
             raise NotImplementedError("state preparation on a batched b200fock circuit is not supported yet")
         self._flush()
+        self._canonicalize()
         D, n, k = self._trunc, self._num_modes, len(modes)
         pure_shape, mixed_shape = (D,) * k, (D,) * (2 * k)
         state = np.asarray(state)
@@ -621,6 +760,7 @@ class DeviceCircuit:
         if n == k:
             # circuit.py:441-444 fast path (+ the mode permutation of 461-473)
             self._pure = bool(is_ket)
+            self._set_identity_layout()
             src = torch.from_numpy(host.reshape(-1)).to(self.device)
             if modes == list(range(n)):
                 self._buf = src
@@ -736,6 +876,7 @@ class DeviceCircuit:
 
     def host_state(self):
         self._flush()
+        self._canonicalize()
         arr = self._buf.cpu().numpy()
         shape = ([self._B] if self._batched else []) + [self._trunc] * self._axes()
         return arr.reshape(shape)
@@ -746,8 +887,14 @@ class DeviceCircuit:
         self._flush()
         n, D, B = self._num_modes, self._trunc, self._B
         out = torch.empty(B * D ** n, dtype=torch.float64, device=self.device)
-        if self._pure:
+        if self._pure and self._is_canonical():
             L.call("b200_abs2", _ptr(self._buf), _ptr(out), self._buf.numel(), self._stream())
+        elif self._pure:
+            per = self._size()
+            oa = [(B, per, per, per)] if B > 1 else []
+            for i in range(n):
+                oa.append((D, self._stride(i), self._stride(i), D ** (n - 1 - i)))
+            self._gather(self._buf, self._buf, out, oa, flags=L.FLAG_CONJ_B | L.FLAG_REAL_OUT)
         else:
             oa = [(B, self._size(), 0, D ** n)] if B > 1 else []
             for i in range(n):

@@ -19,23 +19,9 @@
 // Replaces Circuit.apply_gate_BLAS (fockbackend/circuit.py:118-217),
 // Circuit.apply_twomode_gate + numba kernels (circuit.py:219-365) and, for the loss
 // channel, Circuit._apply_channel (circuit.py:65-87) of the reference.
-#include "common.cuh"
+#include "blocks.cuh"
 
 namespace b200 {
-
-constexpr int MAX_TASKS = B200_MAX_CUTOFF;
-
-struct SubBlock {
-  int c;        // members (0 = unused)
-  int coef;     // offset of the c x c matrix in the packed table
-  int start_k;  // first member's index on axis 1
-  int start_l;  // first member's index on axis 2
-};
-struct TaskTable {
-  int ntasks;
-  int dl;  // per-member step on axis 2: -1 (SUM), +1 (DIFF), 0 (SINGLE)
-  SubBlock sub[MAX_TASKS][2];
-};
 
 struct Geometry {
   // slice s (0 <= s < n_slices) -> element offset
@@ -49,55 +35,6 @@ struct Geometry {
   int coef_count;  // packed entries to stage in shared memory
   int conj;
 };
-
-template <int C>
-__device__ __forceinline__ void block_apply(cplx* __restrict__ p, long long step,
-                                            const cplx* __restrict__ M) {
-  cplx x[C];
-#pragma unroll
-  for (int j = 0; j < C; ++j) x[j] = p[j * step];
-#pragma unroll 2
-  for (int a = 0; a < C; ++a) {
-    cplx acc = make_double2(0.0, 0.0);
-#pragma unroll
-    for (int j = 0; j < C; ++j) cfma(acc, M[a * C + j], x[j]);
-    p[a * step] = acc;
-  }
-}
-
-// any block size (cutoffs above B200_MAX_FAST_CUTOFF): amplitudes staged in local memory
-__device__ __noinline__ void block_apply_dyn(int c, cplx* __restrict__ p, long long step,
-                                             const cplx* __restrict__ M) {
-  cplx x[B200_MAX_CUTOFF];
-  for (int j = 0; j < c; ++j) x[j] = p[j * step];
-  for (int a = 0; a < c; ++a) {
-    cplx acc = make_double2(0.0, 0.0);
-    for (int j = 0; j < c; ++j) cfma(acc, M[a * c + j], x[j]);
-    p[a * step] = acc;
-  }
-}
-
-__device__ __forceinline__ void block_dispatch(int c, cplx* p, long long step, const cplx* M) {
-  switch (c) {
-    case 1: block_apply<1>(p, step, M); break;
-    case 2: block_apply<2>(p, step, M); break;
-    case 3: block_apply<3>(p, step, M); break;
-    case 4: block_apply<4>(p, step, M); break;
-    case 5: block_apply<5>(p, step, M); break;
-    case 6: block_apply<6>(p, step, M); break;
-    case 7: block_apply<7>(p, step, M); break;
-    case 8: block_apply<8>(p, step, M); break;
-    case 9: block_apply<9>(p, step, M); break;
-    case 10: block_apply<10>(p, step, M); break;
-    case 11: block_apply<11>(p, step, M); break;
-    case 12: block_apply<12>(p, step, M); break;
-    case 13: block_apply<13>(p, step, M); break;
-    case 14: block_apply<14>(p, step, M); break;
-    case 15: block_apply<15>(p, step, M); break;
-    case 16: block_apply<16>(p, step, M); break;
-    default: block_apply_dyn(c, p, step, M); break;
-  }
-}
 
 constexpr int APPLY_THREADS = 256;
 
@@ -210,42 +147,6 @@ __global__ void k_mul_tables(long long n, const cplx* __restrict__ a, const cplx
 }
 
 // ---- host side ------------------------------------------------------------------------------
-static void build_tasks(int rule, int D, TaskTable& tt) {
-  memset(&tt, 0, sizeof(tt));
-  if (rule == B200_RULE_SINGLE) {
-    tt.ntasks = 1;
-    tt.dl = 0;
-    tt.sub[0][0] = SubBlock{D, 0, 0, 0};
-    return;
-  }
-  tt.dl = (rule == B200_RULE_SUM) ? -1 : +1;
-  auto make = [&](int b) {
-    int lo = blk_lo(b, D);
-    SubBlock s;
-    s.c = blk_size(b, D);
-    s.coef = blk_off(b, D);
-    s.start_k = lo;
-    s.start_l = (rule == B200_RULE_SUM) ? (b - lo) : (lo - (b - (D - 1)));
-    return s;
-  };
-  // blocks sorted by size: lower half b (size b+1) and upper half 2D-2-b (same size);
-  // the i-th smallest is paired with the i-th largest so that every task holds D amplitudes.
-  int order[2 * B200_MAX_CUTOFF];
-  int n = 0;
-  for (int b = 0; b <= D - 2; ++b) {
-    order[n++] = b;
-    order[n++] = 2 * D - 2 - b;
-  }
-  int t = 0;
-  tt.sub[t++][0] = make(D - 1);  // the middle block, D members
-  for (int i = 0; i < n / 2; ++i) {
-    tt.sub[t][0] = make(order[n - 1 - i]);
-    tt.sub[t][1] = make(order[i]);
-    ++t;
-  }
-  tt.ntasks = t;
-}
-
 static int launch_blocks(cplx* state, const cplx* coef, Geometry& g, const TaskTable& tt, int nbatch,
                          cudaStream_t st) {
   size_t smem = (size_t)g.coef_count * sizeof(cplx);

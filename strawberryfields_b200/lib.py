@@ -47,6 +47,21 @@ class GatherDesc(C.Structure):
     ]
 
 
+class TileOp(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int),
+        ("axis1", C.c_int),
+        ("axis2", C.c_int),
+        ("conj", C.c_int),
+        ("coef_offset", C.c_int64),
+    ]
+
+
+TILE_DIAG = 3
+TILE_MAX_OPS = 16
+MAX_FAST_CUTOFF = 16
+SMEM_LIMIT = 227 * 1024
+
 _P, _I, _L, _D = C.c_void_p, C.c_int, C.c_int64, C.c_double
 
 # name -> argtypes (every function returns int unless listed in _RESTYPES)
@@ -68,6 +83,9 @@ SIGNATURES = {
     "b200_apply_gate2": [_P, _L, _I, _L, _L, _I, _P, _I, _I, _L, _L, _P],
     "b200_apply_diag": [_P, _L, _I, _L, _L, _P, _I, _I, _L, _L, _P],
     "b200_apply_diag_multi": [_P, _L, _I, _I, _P, _P, _P, _I, _L, _L, _P],
+    "b200_tile_groups": [_I],
+    "b200_tile_smem_bytes": [_I, _L],
+    "b200_apply_tile_pass": [_P, _L, _I, _L, _L, C.POINTER(TileOp), _I, C.POINTER(C.c_int), _P, _L, _I, _L, _L, _P],
     "b200_gather_reduce": [C.POINTER(GatherDesc), _P, _P, _P, _I, _P, _P],
     "b200_fill_zero": [_P, _L, _P],
     "b200_set_element": [_P, _L, _D, _D, _P],
@@ -79,6 +97,7 @@ _RESTYPES = {
     "b200_last_error": C.c_char_p,
     "b200_packed_size": C.c_int64,
     "b200_launch_count": C.c_int64,
+    "b200_tile_smem_bytes": C.c_int64,
     "b200_reset_launch_count": None,
 }
 
@@ -122,6 +141,13 @@ def check(rc: int, what: str = ""):
 def call(name: str, *args):
     """Call an int-returning entry point and raise on a non-zero status."""
     check(getattr(load(), name)(*args), name)
+
+
+def tile_smem_bytes(D: int, coef_count: int) -> int:
+    """shared memory of one b200_apply_tile_pass CTA (mirrors b200_tile_smem_bytes)"""
+    s1 = D | 1
+    s0 = (D * s1) | 1
+    return (max(1, 32 // D) * ((D * s0) | 1) + coef_count) * 16
 
 
 def packed_size(D: int) -> int:

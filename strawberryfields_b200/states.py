@@ -103,14 +103,12 @@ class _FockStateMixin:
         if max(n) >= self._cutoff:
             raise ValueError("Can't get distribution beyond truncation level")
         v = self._view
-        D = self._cutoff
+        v._flush()
         per = v._size()
         if self._pure:
-            idx = sum(int(x) * D ** (self._modes - 1 - i) for i, x in enumerate(n))
+            idx = sum(int(x) * v._stride(i) for i, x in enumerate(n))
         else:
-            idx = sum(int(x) * (D ** (2 * self._modes - 1 - 2 * i) + D ** (2 * self._modes - 2 - 2 * i))
-                      for i, x in enumerate(n))
-        v._flush()
+            idx = sum(int(x) * (v._stride(2 * i) + v._stride(2 * i + 1)) for i, x in enumerate(n))
         vals = v._buf[idx::per].cpu().numpy()
         res = np.abs(vals) ** 2 if self._pure else vals.real
         return res if self._batched else res[0]

@@ -261,6 +261,54 @@ class FakeLib:
         self.launches += 1
         return 0
 
+    # -- tile pass
+    def b200_tile_groups(self, D):
+        return max(1, 32 // D)
+
+    def b200_tile_smem_bytes(self, D, coef_count):
+        s1 = D | 1
+        s0 = (D * s1) | 1
+        return (max(1, 32 // D) * ((D * s0) | 1) + coef_count) * 16
+
+    def b200_apply_tile_pass(self, state, total, D, stride0, stride1, ops, nops, out_perm, coef, coef_count,
+                             nb, sbs, cbs, stream):
+        if D < 2 or D > 16 or stride1 % D or stride0 % (D * stride1) or total % (D * stride0):
+            return -1
+        if self.b200_tile_smem_bytes(D, coef_count) > 227 * 1024:
+            return -2
+        lo, mid, hi = stride1 // D, stride0 // (D * stride1), total // (D * stride0)
+        pos = [1, 3, 5]
+        letters = "abcdef"
+        for b in range(nb):
+            st = _c(_addr(state) + 16 * b * sbs, total)
+            cur = st.reshape(hi, D, mid, D, lo, D).copy()
+            cf = _c(_addr(coef) + 16 * b * cbs, coef_count) if coef_count else None
+            for o in range(nops):
+                op = ops[o]
+                off = op.coef_offset
+                if op.kind == 3:
+                    t = cf[off:off + D]
+                    t = t.conj() if op.conj else t
+                    shape = [1] * 6
+                    shape[pos[op.axis1]] = D
+                    cur = cur * t.reshape(shape)
+                elif op.kind == 0:
+                    U = cf[off:off + D * D].reshape(D, D)
+                    U = U.conj() if op.conj else U
+                    cur = np.moveaxis(np.tensordot(U, cur, axes=(1, pos[op.axis1])), 0, pos[op.axis1])
+                else:
+                    T = unpack(cf[off:off + packed_size(D)], op.kind, D)
+                    T = T.conj() if op.conj else T
+                    a1, a2 = pos[op.axis1], pos[op.axis2]
+                    cur = np.moveaxis(np.tensordot(T, cur, axes=([1, 3], [a1, a2])), [0, 1], [a1, a2])
+            order = list(range(6))
+            for k in range(3):
+                order[pos[out_perm[k]]] = pos[k]
+            st[:] = np.ascontiguousarray(cur.transpose(order)).reshape(-1)
+        del letters
+        self.launches += 1
+        return 0
+
     # -- gather
     def b200_gather_reduce(self, desc, A, B, Cc, flags, part, stream):
         d = desc._obj

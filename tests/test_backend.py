@@ -43,7 +43,7 @@ def host_backend(request, monkeypatch):
     return make
 
 
-@pytest.mark.parametrize("fuse", [True, False])
+@pytest.mark.parametrize("fuse", [True, "fold", False])
 @pytest.mark.parametrize("script", scripts.all_scripts(), ids=lambda s: s[0])
 def test_script_matches_reference_fixture(script, fuse, host_backend, golden_dir, request):
     if script[0] == "boson_sampling_d7" and request.node.callspec.params["host_backend"] == "host":
@@ -192,3 +192,33 @@ def test_reset_changes_cutoff(host_backend):
     assert be.get_cutoff_dim() == 6
     assert be.is_vacuum(0.0)
     assert be.state().ket().shape == (6, 6)
+
+
+def test_tile_mode_fuses_gates_into_fewer_launches(monkeypatch, golden_dir):
+    """With fuse=True the 35-gate compiled interferometer program runs as a handful of
+    b200_apply_tile_pass launches and no per-gate pass; same ket as the reference."""
+    from strawberryfields_b200 import circuit, lib
+    from strawberryfields_b200.backend import B200FockBackend
+
+    log = []
+
+    class Spy(FakeLib):
+        def __getattribute__(self, name):
+            attr = FakeLib.__getattribute__(self, name)
+            if name.startswith("b200_apply"):
+                log.append(name)
+            return attr
+
+    monkeypatch.setattr(lib, "_lib", Spy())
+    monkeypatch.setattr(circuit, "_TEST_HOST_MODE", True)
+    with open(os.path.join(golden_dir, "interferometer_n5.json")) as f:
+        gl = json.load(f)["gates"]
+    be = B200FockBackend()
+    be.begin_circuit(5, cutoff_dim=5)
+    for g in gl:
+        getattr(be, g[0])(*g[1:])
+    ket = be.state().ket()
+    ref = np.load(os.path.join(golden_dir, "ref_interferometer_n5_d5.npz"))["data"]
+    assert np.abs(ket - ref).max() < TOL
+    assert set(log) == {"b200_apply_tile_pass"}
+    assert len(log) < len(gl) / 2

@@ -256,3 +256,70 @@ def test_bad_arguments_fail_loudly(lib, torch_mod):
         lib.call("b200_apply_gate1", _p(st), 1, 200, 1, _p(st), 0, 1, 16, 0, None)
     with pytest.raises(lib.B200Error):
         lib.call("b200_apply_gate2", _p(st), 16, 2, 3, 1, lib.RULE_SUM, _p(st), 0, 1, 16, 0, None)
+
+
+# ---------------------------------------------------------------------------- tile pass
+@pytest.mark.parametrize("D", [2, 3, 4, 5, 7, 8, 10, 11, 12, 13, 16])
+def test_tile_pass_matches_numpy_double(lib, torch_mod, D):
+    """b200_apply_tile_pass (cp.async-staged tiles, op list, output permutation) against the
+    numpy double of the ABI, for every cutoff the kernel is instantiated for."""
+    from fake_lib import FakeLib, pack
+
+    torch = torch_mod
+    rs = np.random.RandomState(200 + D)
+    n = 5 if D <= 5 else 4
+    total = D ** n
+    psi = _rand(rs, total)
+    P = lib.packed_size(D)
+    U = _rand(rs, D, D)
+    d = np.exp(1j * rs.uniform(0, 6, D))
+    bs = pack(og.beamsplitter(0.7, 0.3, D), lib.RULE_SUM, D)
+    s2 = pack(og.two_mode_squeeze(0.3, 0.9, D), lib.RULE_DIFF, D)
+    coef = np.concatenate([U.reshape(-1), d, bs, s2, U.reshape(-1)])
+    offs = [0, D * D, D * D + D, D * D + D + P, D * D + D + 2 * P]
+    fake = FakeLib()
+    cases = [(0, 1), (0, n - 2), (n - 3, n - 2)]
+    perms = [(0, 1, 2), (2, 0, 1), (1, 2, 0), (0, 2, 1)]
+    for ci, (p0, p1) in enumerate(cases):
+        ops = (lib.TileOp * 6)()
+        spec = [(lib.RULE_SINGLE, 0, 0, 0, offs[0]), (lib.TILE_DIAG, 2, 0, 1, offs[1]),
+                (lib.RULE_SUM, 1, 2, 0, offs[2]), (lib.RULE_DIFF, 2, 0, 1, offs[3]),
+                (lib.RULE_SINGLE, 2, 0, 1, offs[4]), (lib.RULE_SUM, 0, 1, 0, offs[2])]
+        for i, (k, a1, a2, cj, off) in enumerate(spec):
+            ops[i].kind, ops[i].axis1, ops[i].axis2, ops[i].conj, ops[i].coef_offset = k, a1, a2, cj, off
+        perm = (C.c_int * 3)(*perms[ci % len(perms)])
+        s0, s1 = D ** (n - 1 - p0), D ** (n - 1 - p1)
+        st = _dev(torch, psi)
+        cf = _dev(torch, coef)
+        lib.call("b200_apply_tile_pass", _p(st), total, D, s0, s1, ops, 6, perm, _p(cf), coef.size, 1, total, 0,
+                 None)
+        want = psi.copy()
+        cfh = coef.copy()
+        rc = fake.b200_apply_tile_pass(C.c_void_p(want.ctypes.data), total, D, s0, s1, ops, 6, perm,
+                                       C.c_void_p(cfh.ctypes.data), coef.size, 1, total, 0, None)
+        assert rc == 0
+        assert np.abs(st.cpu().numpy() - want).max() < 1e-11
+
+
+def test_tile_pass_batched_and_ragged(lib, torch_mod):
+    from fake_lib import FakeLib, pack
+
+    torch = torch_mod
+    rs = np.random.RandomState(77)
+    D, n, B = 10, 4, 3  # 10 tiles per batch entry: not a multiple of the 3 tiles a CTA stages
+    total = D ** n
+    psi = _rand(rs, B * total)
+    P = lib.packed_size(D)
+    coef = np.concatenate([np.concatenate([pack(og.beamsplitter(0.2 + 0.3 * b, 0.1 * b, D), lib.RULE_SUM, D),
+                                           _rand(rs, D * D)]) for b in range(B)])
+    per = P + D * D
+    ops = (lib.TileOp * 2)()
+    ops[0].kind, ops[0].axis1, ops[0].axis2, ops[0].conj, ops[0].coef_offset = lib.RULE_SUM, 0, 2, 0, 0
+    ops[1].kind, ops[1].axis1, ops[1].axis2, ops[1].conj, ops[1].coef_offset = lib.RULE_SINGLE, 1, 0, 0, P
+    perm = (C.c_int * 3)(1, 0, 2)
+    st, cf = _dev(torch, psi), _dev(torch, coef)
+    lib.call("b200_apply_tile_pass", _p(st), total, D, D ** 3, D ** 1, ops, 2, perm, _p(cf), per, B, total, per, None)
+    want, cfh = psi.copy(), coef.copy()
+    FakeLib().b200_apply_tile_pass(C.c_void_p(want.ctypes.data), total, D, D ** 3, D ** 1, ops, 2, perm,
+                                   C.c_void_p(cfh.ctypes.data), per, B, total, per, None)
+    assert np.abs(st.cpu().numpy() - want).max() < 1e-11
