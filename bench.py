@@ -67,7 +67,7 @@ class ClockSampler:
             os.close(fd)
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                 "-lms", "50"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -178,8 +178,9 @@ def b200_arm(args):
         torch.cuda.synchronize()
 
     # ---- device-resident leg: `value` ---------------------------------------------------
+    fuse = {"tile": True, "fold": "fold", "off": False}[args.fuse]
     be = B200FockBackend()
-    be.begin_circuit(n_modes, cutoff_dim=D)
+    be.begin_circuit(n_modes, cutoff_dim=D, fuse=fuse)
     for _ in range(args.warmup):
         W.run_calls(be, calls)
         be.circuit._flush()
@@ -216,14 +217,19 @@ def b200_arm(args):
         d[0] += nbytes
         d[1] += t
         d[2] += 1
-    dom = [(tag, v) for tag, v in by_tag.items() if tag.startswith("gate")]
-    dom_bytes = sum(v[0] for _, v in dom)
-    dom_time = sum(v[1] for _, v in dom)
-    dom_n = sum(v[2] for _, v in dom)
+    kernels = {"k_tile_pass": "tile", "k_apply_blocks": "gate", "k_apply_diag": "diag"}
+    groups = {}
+    for kname, prefix in kernels.items():
+        sel = [v for tag, v in by_tag.items() if tag.startswith(prefix)]
+        if sel:
+            groups[kname] = (sum(v[0] for v in sel), sum(v[1] for v in sel), sum(v[2] for v in sel))
+    dom_kernel = max(groups, key=lambda k: groups[k][1])
+    dom_bytes, dom_time, dom_n = groups[dom_kernel]
     peak, peak_src = measured_peaks()
     achieved = dom_bytes / dom_time / 1e9 if dom_time > 0 else 0.0
     roofline = {
-        "kernel": "k_apply_blocks", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "kernel": dom_kernel, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "share_of_step_time": dom_time / max(sum(g[1] for g in groups.values()), 1e-12),
         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
         "launches_per_step": dom_n, "avg_launch_ms": dom_time / max(dom_n, 1) * 1e3,
         "algorithmic_bytes_per_launch": 32 * elements,
@@ -253,7 +259,7 @@ def b200_arm(args):
     def e2e_step():
         dev_params = pinned.to("cuda", non_blocking=True)  # H2D of the step's inputs
         be2 = B200FockBackend()
-        be2.begin_circuit(n_modes, cutoff_dim=D)
+        be2.begin_circuit(n_modes, cutoff_dim=D, fuse=fuse)
         for i, c in enumerate(calls):
             modes = [x for x in c[1:] if isinstance(x, int)]
             getattr(be2, c[0])(*([DeviceParams(dev_params[i])] + ([None] if c[0] != "rotation" else []) + modes))
@@ -299,6 +305,7 @@ def b200_arm(args):
                 "parallelism": "replicas x%d" % world if world > 1 else "single GPU",
                 "l2": "state %.2f GB per GPU > 126 MB L2: every pass streams from HBM" % (elements * 16 / 1e9),
                 "passes_per_step": sum(v[2] for v in by_tag.values()),
+                "gate_queue": args.fuse,
             },
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
             "hbm_GBps_whole_step": 32 * elements * sum(v[2] for v in by_tag.values()) * args.steps
@@ -315,12 +322,14 @@ def b200_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--modes", type=int, default=8)
     ap.add_argument("--cutoff", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fuse", default="tile", choices=["tile", "fold", "off"],
+                    help="gate queue: tile passes (default), diagonal folding only, or one pass per gate")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
