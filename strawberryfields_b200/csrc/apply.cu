@@ -11,10 +11,12 @@
 // A "slice" fixes all other indices.  Work is cut into tasks of exactly D amplitudes per
 // slice (the middle block alone, every other block paired with its complement), so a
 // two-mode gate has the same shape as a one-mode gate: N/D tasks, each loading D
-// amplitudes into registers, multiplying by small dense matrices broadcast from shared
-// memory, and storing D amplitudes back in place.  Lanes of a warp run over consecutive
-// slices (the fastest remaining index), which makes every load/store a run of
-// consecutive 16-byte amplitudes whenever the inner stride allows.
+// amplitudes into registers (all D loads in flight before the first FMA), multiplying by
+// small dense matrices broadcast from shared memory, and storing D amplitudes back in
+// place.  Lanes of a warp run over consecutive slices (the fastest remaining index), which
+// makes every load/store a run of consecutive 16-byte amplitudes whenever the inner stride
+// allows.  The cutoff is a template parameter (2..16) so that the register file holds
+// exactly D amplitudes; larger cutoffs take a local-memory path.
 //
 // Replaces Circuit.apply_gate_BLAS (fockbackend/circuit.py:118-217),
 // Circuit.apply_twomode_gate + numba kernels (circuit.py:219-365) and, for the loss
@@ -38,21 +40,68 @@ struct Geometry {
 
 constexpr int APPLY_THREADS = 256;
 
+// one task = two blocks of C0 + C1 = D amplitudes (C1 = 0: a single block)
+template <int C0, int C1>
+__device__ __forceinline__ void task_apply(cplx* __restrict__ p0, cplx* __restrict__ p1, long long step,
+                                           const cplx* __restrict__ M0, const cplx* __restrict__ M1) {
+  cplx x0[C0];
+  cplx x1[C1 > 0 ? C1 : 1];
+#pragma unroll
+  for (int j = 0; j < C0; ++j) x0[j] = p0[j * step];
+#pragma unroll
+  for (int j = 0; j < C1; ++j) x1[j] = p1[j * step];
+#pragma unroll 2
+  for (int a = 0; a < C0; ++a) {
+    cplx acc = make_double2(0.0, 0.0);
+#pragma unroll
+    for (int j = 0; j < C0; ++j) cfma(acc, M0[a * C0 + j], x0[j]);
+    p0[a * step] = acc;
+  }
+#pragma unroll 2
+  for (int a = 0; a < C1; ++a) {
+    cplx acc = make_double2(0.0, 0.0);
+#pragma unroll
+    for (int j = 0; j < C1; ++j) cfma(acc, M1[a * C1 + j], x1[j]);
+    p1[a * step] = acc;
+  }
+}
+
+template <int D>
+__device__ __forceinline__ void task_dispatch(int c0, cplx* p0, cplx* p1, long long step, const cplx* M0,
+                                              const cplx* M1) {
+#define B200_CASE(N) \
+  case N:            \
+    if constexpr (N <= D) task_apply<N, D - N>(p0, p1, step, M0, M1); \
+    break;
+  switch (c0) {
+    B200_CASE(1) B200_CASE(2) B200_CASE(3) B200_CASE(4) B200_CASE(5) B200_CASE(6) B200_CASE(7) B200_CASE(8)
+    B200_CASE(9) B200_CASE(10) B200_CASE(11) B200_CASE(12) B200_CASE(13) B200_CASE(14) B200_CASE(15)
+    B200_CASE(16)
+    default: break;
+  }
+#undef B200_CASE
+}
+
+__device__ __forceinline__ void stage_coef(cplx* M, const cplx* cg, int n, int conj) {
+  for (int i = threadIdx.x; i < n; i += APPLY_THREADS) {
+    cplx v = cg[i];
+    if (conj) v.y = -v.y;
+    M[i] = v;
+  }
+  __syncthreads();
+}
+
 // grid: (slice groups, 1, nbatch).  CTA = 8 warps; warp-task = (32 consecutive slices, task).
 // A CTA owns `groups_per_cta` slice groups x all tasks and its warps stride over them.
-__global__ void __launch_bounds__(APPLY_THREADS)
-k_apply_blocks(cplx* __restrict__ state, const cplx* __restrict__ coef, Geometry g, TaskTable tt,
+// D = 0: any cutoff (local-memory blocks).
+template <int D>
+__global__ void __launch_bounds__(APPLY_THREADS, (D >= 1 && D <= 12) ? 3 : 2)
+k_apply_blocks(cplx* __restrict__ state, const cplx* __restrict__ coef, const Geometry g, const TaskTable tt,
                int groups_per_cta) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cplx* M = reinterpret_cast<cplx*>(smem_raw);
   const int batch = blockIdx.z;
-  const cplx* cg = coef + (size_t)batch * g.coef_batch_stride;
-  for (int i = threadIdx.x; i < g.coef_count; i += APPLY_THREADS) {
-    cplx v = cg[i];
-    if (g.conj) v.y = -v.y;
-    M[i] = v;
-  }
-  __syncthreads();
+  stage_coef(M, coef + (size_t)batch * g.coef_batch_stride, g.coef_count, g.conj);
 
   cplx* base = state + (size_t)batch * g.state_batch_stride;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -66,58 +115,33 @@ k_apply_blocks(cplx* __restrict__ state, const cplx* __restrict__ coef, Geometry
     const unsigned i_in = s % g.inner, rest = s / g.inner;
     const unsigned i_mid = rest % g.mid, i_out = rest / g.mid;
     cplx* ps = base + (long long)i_out * g.outer_step + (long long)i_mid * g.mid_step + i_in;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const SubBlock sb = tt.sub[task][h];
-      if (sb.c == 0) continue;
-      block_dispatch(sb.c, ps + sb.start_k * g.stride1 + sb.start_l * g.stride2, step, M + sb.coef);
+    const SubBlock sb0 = tt.sub[task][0], sb1 = tt.sub[task][1];
+    cplx* p0 = ps + sb0.start_k * g.stride1 + sb0.start_l * g.stride2;
+    cplx* p1 = ps + sb1.start_k * g.stride1 + sb1.start_l * g.stride2;
+    if constexpr (D > 0) {
+      task_dispatch<D>(sb0.c, p0, p1, step, M + sb0.coef, M + sb1.coef);
+    } else {
+      block_apply_dyn(sb0.c, p0, step, M + sb0.coef);
+      if (sb1.c) block_apply_dyn(sb1.c, p1, step, M + sb1.coef);
     }
   }
 }
 
 // ---- diagonal gates ---------------------------------------------------------------------
-// state[e] *= tab[digit1(e)] or tab[digit1(e) * D + digit2(e)]
-__global__ void __launch_bounds__(256)
-k_apply_diag(cplx* __restrict__ state, long long total, int D, long long stride1, long long stride2,
-             const cplx* __restrict__ tab, int conj, long long state_batch_stride, long long tab_batch_stride) {
-  __shared__ cplx T[B200_MAX_CUTOFF * B200_MAX_CUTOFF > 1024 ? 1024 : B200_MAX_CUTOFF * B200_MAX_CUTOFF];
-  const int batch = blockIdx.z;
-  const int ntab = stride2 ? D * D : D;
-  const cplx* tg = tab + (size_t)batch * tab_batch_stride;
-  const bool in_smem = ntab <= 1024;
-  if (in_smem) {
-    for (int i = threadIdx.x; i < ntab; i += blockDim.x) {
-      cplx v = tg[i];
-      if (conj) v.y = -v.y;
-      T[i] = v;
-    }
-    __syncthreads();
-  }
-  cplx* base = state + (size_t)batch * state_batch_stride;
-  const long long nthreads = (long long)gridDim.x * blockDim.x;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += nthreads) {
-    int d1 = (int)((e / stride1) % D);
-    int idx = d1;
-    if (stride2) idx = d1 * D + (int)((e / stride2) % D);
-    cplx f;
-    if (in_smem) f = T[idx];
-    else {
-      f = tg[idx];
-      if (conj) f.y = -f.y;
-    }
-    base[e] = cmul(base[e], f);
-  }
-}
-
-struct MultiDiag {
+// Index arithmetic is 32-bit whenever the state has fewer than 2^32 elements (always true for
+// one launch on one GPU: 180 GB / 16 B = 1.1e10 would need it, 1e9-1e10-element shards do not).
+template <typename I>
+struct DiagAxes {
   int naxes;
   int conj[B200_MAX_AXES];
-  long long stride[B200_MAX_AXES];
+  I stride[B200_MAX_AXES];
 };
+
 // state[e] *= prod_k tabs[k][digit_k(e)] -- every pending diagonal gate in one pass
+template <typename I>
 __global__ void __launch_bounds__(256)
-k_apply_diag_multi(cplx* __restrict__ state, long long total, int D, MultiDiag md,
-                   const cplx* __restrict__ tabs, long long state_batch_stride, long long tab_batch_stride) {
+k_apply_diag_multi(cplx* __restrict__ state, I total, int D, const DiagAxes<I> md, const cplx* __restrict__ tabs,
+                   long long state_batch_stride, long long tab_batch_stride) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cplx* T = reinterpret_cast<cplx*>(smem_raw);
   const int batch = blockIdx.z;
@@ -129,10 +153,31 @@ k_apply_diag_multi(cplx* __restrict__ state, long long total, int D, MultiDiag m
   }
   __syncthreads();
   cplx* base = state + (size_t)batch * state_batch_stride;
-  const long long nthreads = (long long)gridDim.x * blockDim.x;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += nthreads) {
-    cplx f = T[(int)((e / md.stride[0]) % D)];
-    for (int k = 1; k < md.naxes; ++k) f = cmul(f, T[k * D + (int)((e / md.stride[k]) % D)]);
+  const I nthreads = (I)gridDim.x * blockDim.x;
+  const I uD = (I)D;
+  for (I e = (I)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += nthreads) {
+    cplx v = base[e];
+    cplx f = T[(int)((e / md.stride[0]) % uD)];
+    for (int k = 1; k < md.naxes; ++k) f = cmul(f, T[k * D + (int)((e / md.stride[k]) % uD)]);
+    base[e] = cmul(v, f);
+  }
+}
+
+// state[e] *= tab[digit1(e) * D + digit2(e)]  (two-axis diagonal: cross-Kerr)
+template <typename I>
+__global__ void __launch_bounds__(256)
+k_apply_diag_pair(cplx* __restrict__ state, I total, int D, I stride1, I stride2, const cplx* __restrict__ tab,
+                  int conj, long long state_batch_stride, long long tab_batch_stride) {
+  const int batch = blockIdx.z;
+  const cplx* tg = tab + (size_t)batch * tab_batch_stride;
+  cplx* base = state + (size_t)batch * state_batch_stride;
+  const I nthreads = (I)gridDim.x * blockDim.x;
+  const I uD = (I)D;
+  for (I e = (I)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += nthreads) {
+    int idx = (int)((e / stride1) % uD);
+    if (stride2) idx = idx * D + (int)((e / stride2) % uD);
+    cplx f = __ldg(&tg[idx]);
+    if (conj) f.y = -f.y;
     base[e] = cmul(base[e], f);
   }
 }
@@ -147,20 +192,44 @@ __global__ void k_mul_tables(long long n, const cplx* __restrict__ a, const cplx
 }
 
 // ---- host side ------------------------------------------------------------------------------
-static int launch_blocks(cplx* state, const cplx* coef, Geometry& g, const TaskTable& tt, int nbatch,
+template <int D>
+static cudaError_t launch_blocks_d(cplx* state, const cplx* coef, const Geometry& g, const TaskTable& tt,
+                                   dim3 grid, size_t smem, int gpc, cudaStream_t st) {
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k_apply_blocks<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  k_apply_blocks<D><<<grid, APPLY_THREADS, smem, st>>>(state, coef, g, tt, gpc);
+  return cudaSuccess;
+}
+
+static int launch_blocks(int D, cplx* state, const cplx* coef, Geometry& g, const TaskTable& tt, int nbatch,
                          cudaStream_t st) {
   size_t smem = (size_t)g.coef_count * sizeof(cplx);
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(k_apply_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return fail((int)e, "apply: shared memory opt-in failed: %s", cudaGetErrorString(e));
-  }
   unsigned n_groups = (g.n_slices + 31u) / 32u;
   // ~16 warp-tasks per CTA: two per warp, enough to amortise staging the gate table
   int gpc = tt.ntasks >= 16 ? 1 : (16 + tt.ntasks - 1) / tt.ntasks;
   unsigned n_cta = (n_groups + gpc - 1) / gpc;
   dim3 grid(n_cta, 1, nbatch);
-  k_apply_blocks<<<grid, APPLY_THREADS, smem, st>>>(state, coef, g, tt, gpc);
+  cudaError_t e = cudaSuccess;
+#define B200_LAUNCH(N) \
+  case N:              \
+    e = launch_blocks_d<N>(state, coef, g, tt, grid, smem, gpc, st); \
+    break;
+  switch (D <= B200_MAX_FAST_CUTOFF ? D : 0) {
+    B200_LAUNCH(1) B200_LAUNCH(2) B200_LAUNCH(3) B200_LAUNCH(4) B200_LAUNCH(5) B200_LAUNCH(6) B200_LAUNCH(7)
+    B200_LAUNCH(8) B200_LAUNCH(9) B200_LAUNCH(10) B200_LAUNCH(11) B200_LAUNCH(12) B200_LAUNCH(13)
+    B200_LAUNCH(14) B200_LAUNCH(15) B200_LAUNCH(16)
+    default: e = launch_blocks_d<0>(state, coef, g, tt, grid, smem, gpc, st); break;
+  }
+#undef B200_LAUNCH
+  if (e != cudaSuccess) return fail((int)e, "apply: shared memory opt-in failed: %s", cudaGetErrorString(e));
   return cuda_status("apply_blocks");
+}
+
+static unsigned diag_blocks(long long total) {
+  long long want = (total + 255) / 256;
+  return (unsigned)(want < 148 * 16 ? want : 148 * 16);
 }
 
 }  // namespace b200
@@ -190,7 +259,7 @@ int b200_apply_gate1(b200_c128* state_dev, int64_t outer, int D, int64_t inner, 
   g.conj = conj;
   TaskTable tt;
   build_tasks(B200_RULE_SINGLE, D, tt);
-  return launch_blocks((cplx*)state_dev, (const cplx*)U_dev, g, tt, nbatch, (cudaStream_t)stream);
+  return launch_blocks(D, (cplx*)state_dev, (const cplx*)U_dev, g, tt, nbatch, (cudaStream_t)stream);
 }
 
 int b200_apply_gate2(b200_c128* state_dev, int64_t total, int D, int64_t stride1, int64_t stride2, int rule,
@@ -218,7 +287,7 @@ int b200_apply_gate2(b200_c128* state_dev, int64_t total, int D, int64_t stride1
   g.conj = conj;
   TaskTable tt;
   build_tasks(rule, D, tt);
-  return launch_blocks((cplx*)state_dev, (const cplx*)packed_dev, g, tt, nbatch, (cudaStream_t)stream);
+  return launch_blocks(D, (cplx*)state_dev, (const cplx*)packed_dev, g, tt, nbatch, (cudaStream_t)stream);
 }
 
 int b200_apply_diag(b200_c128* state_dev, int64_t total, int D, int64_t stride1, int64_t stride2,
@@ -227,12 +296,15 @@ int b200_apply_diag(b200_c128* state_dev, int64_t total, int D, int64_t stride1,
   B200_CHECK_ARG(state_dev && tab_dev, "apply_diag: null pointer");
   B200_CHECK_ARG(D >= 1 && D <= B200_MAX_CUTOFF && total >= 1 && stride1 >= 1 && stride2 >= 0 && nbatch >= 1,
                  "apply_diag: bad geometry");
-  long long want = (total + 255) / 256;
-  unsigned blocks = (unsigned)(want < 148 * 16 ? want : 148 * 16);
-  dim3 grid(blocks, 1, nbatch);
-  k_apply_diag<<<grid, 256, 0, (cudaStream_t)stream>>>((cplx*)state_dev, total, D, stride1, stride2,
-                                                       (const cplx*)tab_dev, conj, state_batch_stride,
-                                                       tab_batch_stride);
+  dim3 grid(diag_blocks(total), 1, nbatch);
+  if (total < (1ll << 32))
+    k_apply_diag_pair<unsigned><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        (cplx*)state_dev, (unsigned)total, D, (unsigned)stride1, (unsigned)stride2, (const cplx*)tab_dev, conj,
+        state_batch_stride, tab_batch_stride);
+  else
+    k_apply_diag_pair<unsigned long long><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        (cplx*)state_dev, (unsigned long long)total, D, (unsigned long long)stride1, (unsigned long long)stride2,
+        (const cplx*)tab_dev, conj, state_batch_stride, tab_batch_stride);
   return cuda_status("apply_diag");
 }
 
@@ -242,20 +314,29 @@ int b200_apply_diag_multi(b200_c128* state_dev, int64_t total, int D, int naxes,
   B200_CHECK_ARG(state_dev && tabs_dev && strides && conj_flags, "apply_diag_multi: null pointer");
   B200_CHECK_ARG(naxes >= 1 && naxes <= B200_MAX_AXES, "apply_diag_multi: bad axis count");
   B200_CHECK_ARG(D >= 1 && D <= B200_MAX_CUTOFF && total >= 1 && nbatch >= 1, "apply_diag_multi: bad geometry");
-  MultiDiag md;
-  md.naxes = naxes;
-  for (int k = 0; k < naxes; ++k) {
-    B200_CHECK_ARG(strides[k] >= 1, "apply_diag_multi: bad stride");
-    md.stride[k] = strides[k];
-    md.conj[k] = conj_flags[k];
-  }
-  long long want = (total + 255) / 256;
-  unsigned blocks = (unsigned)(want < 148 * 16 ? want : 148 * 16);
-  dim3 grid(blocks, 1, nbatch);
+  for (int k = 0; k < naxes; ++k) B200_CHECK_ARG(strides[k] >= 1, "apply_diag_multi: bad stride");
+  dim3 grid(diag_blocks(total), 1, nbatch);
   size_t smem = (size_t)naxes * D * sizeof(cplx);
-  k_apply_diag_multi<<<grid, 256, smem, (cudaStream_t)stream>>>((cplx*)state_dev, total, D, md,
-                                                                (const cplx*)tabs_dev, state_batch_stride,
-                                                                tab_batch_stride);
+  if (total < (1ll << 32)) {
+    DiagAxes<unsigned> md;
+    md.naxes = naxes;
+    for (int k = 0; k < naxes; ++k) {
+      md.stride[k] = (unsigned)strides[k];
+      md.conj[k] = conj_flags[k];
+    }
+    k_apply_diag_multi<unsigned><<<grid, 256, smem, (cudaStream_t)stream>>>(
+        (cplx*)state_dev, (unsigned)total, D, md, (const cplx*)tabs_dev, state_batch_stride, tab_batch_stride);
+  } else {
+    DiagAxes<unsigned long long> md;
+    md.naxes = naxes;
+    for (int k = 0; k < naxes; ++k) {
+      md.stride[k] = (unsigned long long)strides[k];
+      md.conj[k] = conj_flags[k];
+    }
+    k_apply_diag_multi<unsigned long long><<<grid, 256, smem, (cudaStream_t)stream>>>(
+        (cplx*)state_dev, (unsigned long long)total, D, md, (const cplx*)tabs_dev, state_batch_stride,
+        tab_batch_stride);
+  }
   return cuda_status("apply_diag_multi");
 }
 

@@ -69,16 +69,24 @@ k_tile_pass(cplx* __restrict__ state, const cplx* __restrict__ coef, const TileP
   const unsigned tile0 = blockIdx.x * (unsigned)P.G;
   const int ntile_here = (int)min((unsigned)P.G, P.ntiles - tile0);
 
-  // ---- stage tiles: D^2 runs of D consecutive amplitudes each ----
-  for (int e = tid; e < ntile_here * D3; e += nthr) {
-    int g = e / D3, r = e - g * D3;
-    int i0 = r / D2, i1 = (r / D) % D, i2 = r % D;
-    unsigned t = tile0 + g;
+  // ---- stage tiles: D^2 runs of D consecutive amplitudes each.  A thread owns one (tile, i1, i2)
+  //      column and walks i0, so the address arithmetic is paid once per D copies; consecutive
+  //      lanes take consecutive i2, i.e. every cp.async instruction covers whole 16*D-byte runs. ----
+  __shared__ long long tile_off[32];
+  if (tid < ntile_here) {
+    unsigned t = tile0 + tid;
     unsigned lo = t % P.LO, rest = t / P.LO;
     unsigned mid = rest % P.MID, hi = rest / P.MID;
-    const cplx* src = base + (long long)hi * (D * P.stride0) + (long long)mid * (D * P.stride1) +
-                      (long long)lo * D + (long long)i0 * P.stride0 + (long long)i1 * P.stride1 + i2;
-    cp_async16(&tile[g * P.tile_elems + i0 * P.s[0] + i1 * P.s[1] + i2], src);
+    tile_off[tid] = (long long)hi * (D * P.stride0) + (long long)mid * (D * P.stride1) + (long long)lo * D;
+  }
+  __syncthreads();
+  for (int c = tid; c < ntile_here * D2; c += nthr) {
+    int g = c / D2, r = c - g * D2;
+    int i1 = r / D, i2 = r - i1 * D;
+    const cplx* src = base + tile_off[g] + (long long)i1 * P.stride1 + i2;
+    cplx* dst = &tile[g * P.tile_elems + i1 * P.s[1] + i2];
+#pragma unroll
+    for (int i0 = 0; i0 < D; ++i0) cp_async16(dst + i0 * P.s[0], src + (long long)i0 * P.stride0);
   }
   // ---- stage coefficients, one range per operator (conjugated here for bra-side operators) ----
   const cplx* cg = coef + (size_t)batch * P.coef_batch_stride;
@@ -98,12 +106,16 @@ k_tile_pass(cplx* __restrict__ state, const cplx* __restrict__ coef, const TileP
   for (int o = 0; o < P.nops; ++o) {
     const TileOpDev op = P.ops[o];
     if (op.kind == TILE_KIND_DIAG) {
-      for (int e = tid; e < ntile_here * D3; e += nthr) {
-        int g = e / D3, r = e - g * D3;
-        int i0 = r / D2, i1 = (r / D) % D, i2 = r % D;
-        int dig = op.a1 == 0 ? i0 : (op.a1 == 1 ? i1 : i2);
-        cplx* p = &tile[g * P.tile_elems + i0 * P.s[0] + i1 * P.s[1] + i2];
-        *p = cmul(*p, M[op.coef + dig]);
+      for (int c = tid; c < ntile_here * D2; c += nthr) {
+        int g = c / D2, r = c - g * D2;
+        int i1 = r / D, i2 = r - i1 * D;
+        cplx* p = &tile[g * P.tile_elems + i1 * P.s[1] + i2];
+        const cplx fixed = M[op.coef + (op.a1 == 1 ? i1 : i2)];
+#pragma unroll
+        for (int i0 = 0; i0 < D; ++i0) {
+          cplx f = op.a1 == 0 ? M[op.coef + i0] : fixed;
+          p[i0 * P.s[0]] = cmul(p[i0 * P.s[0]], f);
+        }
       }
     } else if (op.kind == B200_RULE_SINGLE) {
       // slices = (tile, two other axes); one task; lanes over slices, warps over lane groups
@@ -148,15 +160,16 @@ k_tile_pass(cplx* __restrict__ state, const cplx* __restrict__ coef, const TileP
   long long gs[3] = {P.stride0, P.stride1, 1};
   int ss[3];  // shared stride of the tile axis that lands on global position j
   for (int k = 0; k < 3; ++k) ss[P.out_perm[k]] = P.s[k];
-  for (int e = tid; e < ntile_here * D3; e += nthr) {
-    int g = e / D3, r = e - g * D3;
-    int j0 = r / D2, j1 = (r / D) % D, j2 = r % D;
-    unsigned t = tile0 + g;
-    unsigned lo = t % P.LO, rest = t / P.LO;
-    unsigned mid = rest % P.MID, hi = rest / P.MID;
-    cplx* dst = base + (long long)hi * (D * P.stride0) + (long long)mid * (D * P.stride1) + (long long)lo * D +
-                (long long)j0 * gs[0] + (long long)j1 * gs[1] + j2;
-    *dst = tile[g * P.tile_elems + j0 * ss[0] + j1 * ss[1] + j2 * ss[2]];
+  for (int c = tid; c < ntile_here * D2; c += nthr) {
+    int g = c / D2, r = c - g * D2;
+    int j1 = r / D, j2 = r - j1 * D;
+    cplx* dst = base + tile_off[g] + (long long)j1 * gs[1] + j2;
+    const cplx* src = &tile[g * P.tile_elems + j1 * ss[1] + j2 * ss[2]];
+    cplx v[D];
+#pragma unroll
+    for (int j0 = 0; j0 < D; ++j0) v[j0] = src[j0 * ss[0]];
+#pragma unroll
+    for (int j0 = 0; j0 < D; ++j0) dst[(long long)j0 * gs[0]] = v[j0];
   }
 }
 
