@@ -50,20 +50,8 @@ __device__ __forceinline__ void task_apply(cplx* __restrict__ p0, cplx* __restri
   for (int j = 0; j < C0; ++j) x0[j] = p0[j * step];
 #pragma unroll
   for (int j = 0; j < C1; ++j) x1[j] = p1[j * step];
-#pragma unroll 2
-  for (int a = 0; a < C0; ++a) {
-    cplx acc = make_double2(0.0, 0.0);
-#pragma unroll
-    for (int j = 0; j < C0; ++j) cfma(acc, M0[a * C0 + j], x0[j]);
-    p0[a * step] = acc;
-  }
-#pragma unroll 2
-  for (int a = 0; a < C1; ++a) {
-    cplx acc = make_double2(0.0, 0.0);
-#pragma unroll
-    for (int j = 0; j < C1; ++j) cfma(acc, M1[a * C1 + j], x1[j]);
-    p1[a * step] = acc;
-  }
+  rows_apply<C0>(p0, step, M0, x0);
+  if constexpr (C1 > 0) rows_apply<C1>(p1, step, M1, x1);
 }
 
 template <int D>

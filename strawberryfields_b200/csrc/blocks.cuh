@@ -6,18 +6,55 @@
 
 namespace b200 {
 
+// y = M x for a C x C block with x held in registers; rows are produced two at a time and each
+// row keeps FOUR independent FMA chains (re*re, im*im, re*im, im*re), i.e. eight chains in
+// flight: the FP64 pipe's fixed dependent-issue latency ("wait" stalls in ncu) is covered by
+// instruction-level parallelism instead of by occupancy.
+template <int C, typename IdxT>
+__device__ __forceinline__ void rows_apply(cplx* __restrict__ p, IdxT step, const cplx* __restrict__ M,
+                                           const cplx (&x)[C]) {
+#pragma unroll 1
+  for (int a = 0; a + 1 < C; a += 2) {
+    double axx = 0.0, ayy = 0.0, axy = 0.0, ayx = 0.0;
+    double bxx = 0.0, byy = 0.0, bxy = 0.0, byx = 0.0;
+    const cplx* __restrict__ Ma = M + a * C;
+    const cplx* __restrict__ Mb = Ma + C;
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      const cplx ma = Ma[j], mb = Mb[j], v = x[j];
+      axx = fma(ma.x, v.x, axx);
+      ayy = fma(ma.y, v.y, ayy);
+      axy = fma(ma.x, v.y, axy);
+      ayx = fma(ma.y, v.x, ayx);
+      bxx = fma(mb.x, v.x, bxx);
+      byy = fma(mb.y, v.y, byy);
+      bxy = fma(mb.x, v.y, bxy);
+      byx = fma(mb.y, v.x, byx);
+    }
+    p[a * step] = make_double2(axx - ayy, axy + ayx);
+    p[(a + 1) * step] = make_double2(bxx - byy, bxy + byx);
+  }
+  if (C & 1) {
+    double axx = 0.0, ayy = 0.0, axy = 0.0, ayx = 0.0;
+    const cplx* __restrict__ Ma = M + (C - 1) * C;
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      const cplx ma = Ma[j], v = x[j];
+      axx = fma(ma.x, v.x, axx);
+      ayy = fma(ma.y, v.y, ayy);
+      axy = fma(ma.x, v.y, axy);
+      ayx = fma(ma.y, v.x, ayx);
+    }
+    p[(C - 1) * step] = make_double2(axx - ayy, axy + ayx);
+  }
+}
+
 template <int C, typename IdxT>
 __device__ __forceinline__ void block_apply(cplx* __restrict__ p, IdxT step, const cplx* __restrict__ M) {
   cplx x[C];
 #pragma unroll
   for (int j = 0; j < C; ++j) x[j] = p[j * step];
-#pragma unroll 2
-  for (int a = 0; a < C; ++a) {
-    cplx acc = make_double2(0.0, 0.0);
-#pragma unroll
-    for (int j = 0; j < C; ++j) cfma(acc, M[a * C + j], x[j]);
-    p[a * step] = acc;
-  }
+  rows_apply<C>(p, step, M, x);
 }
 
 // any block size (cutoffs above B200_MAX_FAST_CUTOFF): amplitudes staged in local memory
