@@ -427,9 +427,7 @@ class DeviceCircuit:
         self._own()
         D = self._trunc
         tile_bytes = L.tile_smem_bytes(D, 0)
-        budget = (110 * 1024 - tile_bytes) // 16
-        if budget < L.packed_size(D):
-            budget = (L.SMEM_LIMIT - tile_bytes) // 16
+        budget = (L.SMEM_LIMIT - tile_bytes) // 16  # one persistent CTA per SM owns all shared memory
         passes, phys = S.plan(ops, self._phys, L.TILE_MAX_OPS, budget)
         for p in passes:
             self._launch_tile_pass(p)

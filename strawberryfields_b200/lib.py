@@ -147,7 +147,8 @@ def tile_smem_bytes(D: int, coef_count: int) -> int:
     """shared memory of one b200_apply_tile_pass CTA (mirrors b200_tile_smem_bytes)"""
     s1 = D | 1
     s0 = (D * s1) | 1
-    return (max(1, 32 // D) * ((D * s0) | 1) + coef_count) * 16
+    groups = 1 if D >= 14 else max(1, 32 // D)
+    return (2 * groups * ((D * s0) | 1) + coef_count) * 16  # two buffers: the kernel double-buffers
 
 
 def packed_size(D: int) -> int:

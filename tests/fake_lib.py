@@ -263,12 +263,12 @@ class FakeLib:
 
     # -- tile pass
     def b200_tile_groups(self, D):
-        return max(1, 32 // D)
+        return 1 if D >= 14 else max(1, 32 // D)
 
     def b200_tile_smem_bytes(self, D, coef_count):
         s1 = D | 1
         s0 = (D * s1) | 1
-        return (max(1, 32 // D) * ((D * s0) | 1) + coef_count) * 16
+        return (2 * self.b200_tile_groups(D) * ((D * s0) | 1) + coef_count) * 16
 
     def b200_apply_tile_pass(self, state, total, D, stride0, stride1, ops, nops, out_perm, coef, coef_count,
                              nb, sbs, cbs, stream):
