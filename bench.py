@@ -178,7 +178,7 @@ def b200_arm(args):
         torch.cuda.synchronize()
 
     # ---- device-resident leg: `value` ---------------------------------------------------
-    fuse = {"tile": True, "fold": "fold", "off": False}[args.fuse]
+    fuse = {"tile": "tile", "fold": "fold", "off": False}[args.fuse]
     be = B200FockBackend()
     be.begin_circuit(n_modes, cutoff_dim=D, fuse=fuse)
     for _ in range(args.warmup):
@@ -328,7 +328,7 @@ def main():
     ap.add_argument("--modes", type=int, default=8)
     ap.add_argument("--cutoff", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--fuse", default="tile", choices=["tile", "fold", "off"],
+    ap.add_argument("--fuse", default="fold", choices=["tile", "fold", "off"],
                     help="gate queue: tile passes (default), diagonal folding only, or one pass per gate")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -141,7 +141,7 @@ class B200FockBackend(_Base):
             raise ValueError("batch_size of 1 not supported, please use different batch_size or set batch_size=None")
         self._options = {
             "strict_purity": bool(kwargs.get("strict_purity", False)),
-            "fuse": kwargs.get("fuse", True),  # True: tile passes; "fold": diagonal folding only; False: off
+            "fuse": kwargs.get("fuse", True),  # True|"fold": gate folding; "tile": + multi-gate tile passes; False: off
             "device": kwargs.get("device", None),
         }
         self._init_modes = num_subsystems

@@ -84,7 +84,9 @@ class DeviceCircuit:
         if self._B < 1:
             raise ValueError("batch_size must be a positive integer")
         self._strict = bool(strict_purity)
-        self._fuse = "fold" if fuse == "fold" else bool(fuse)
+        # True / "fold": fold diagonal and same-mode gates, one streaming pass per remaining gate (default);
+        # "tile": additionally group gates into multi-gate tile passes (scheduler.py); False: one pass per gate
+        self._fuse = fuse if fuse in ("tile", "fold") else ("fold" if fuse else False)
         self._scratch = None
         self._part = None
         self._norm_out = torch.zeros(2, dtype=torch.float64, device=self.device)
@@ -376,7 +378,7 @@ class DeviceCircuit:
     def _tile_mode(self):
         """Tile passes need >= 3 tensor axes, a cutoff the tile kernel is instantiated for, and
         fuse=True (fuse="fold" keeps the one-pass-per-gate path with diagonal folding only)."""
-        return (self._fuse is True and 2 <= self._trunc <= L.MAX_FAST_CUTOFF and self._axes() >= 3)
+        return (self._fuse == "tile" and 2 <= self._trunc <= L.MAX_FAST_CUTOFF and self._axes() >= 3)
 
     def _emit_dense(self, U, mode):
         """A dense single-mode operator leaves the fold stage: queue it (tile mode) or apply it."""

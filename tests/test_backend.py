@@ -43,7 +43,7 @@ def host_backend(request, monkeypatch):
     return make
 
 
-@pytest.mark.parametrize("fuse", [True, "fold", False])
+@pytest.mark.parametrize("fuse", [True, "tile", False])
 @pytest.mark.parametrize("script", scripts.all_scripts(), ids=lambda s: s[0])
 def test_script_matches_reference_fixture(script, fuse, host_backend, golden_dir, request):
     if script[0] == "boson_sampling_d7" and request.node.callspec.params["host_backend"] == "host":
@@ -214,7 +214,7 @@ def test_tile_mode_fuses_gates_into_fewer_launches(monkeypatch, golden_dir):
     with open(os.path.join(golden_dir, "interferometer_n5.json")) as f:
         gl = json.load(f)["gates"]
     be = B200FockBackend()
-    be.begin_circuit(5, cutoff_dim=5)
+    be.begin_circuit(5, cutoff_dim=5, fuse="tile")
     for g in gl:
         getattr(be, g[0])(*g[1:])
     ket = be.state().ket()
