@@ -145,7 +145,17 @@ class B200FockBackend(_Base):
             "device": kwargs.get("device", None),
         }
         self._init_modes = num_subsystems
-        self.circuit = DeviceCircuit(num_subsystems, cutoff_dim, pure, batch_size=batch_size, **self._options)
+        shard = kwargs.get("shard", False)
+        if shard:
+            # pure state sharded over the ranks of the (default or given) torch.distributed group
+            from .sharding import ShardedCircuit
+
+            if not pure or batch_size is not None:
+                raise NotImplementedError("sharded b200fock circuits hold unbatched pure states only")
+            group = None if shard is True else shard
+            self.circuit = ShardedCircuit(num_subsystems, cutoff_dim, group=group, **self._options)
+        else:
+            self.circuit = DeviceCircuit(num_subsystems, cutoff_dim, pure, batch_size=batch_size, **self._options)
         self._modemap = ModeMap(num_subsystems)
 
     def add_mode(self, n=1, **kwargs):

@@ -318,8 +318,10 @@ class DeviceCircuit:
         naxes = self._axes()
         nb = U.shape[0]
         pos = self._pos[axis]
-        self._pass("gate1/axis%d" % (naxes - 1 - pos), "b200_apply_gate1", _ptr(self._buf), D ** pos, D, D ** (naxes - 1 - pos), _ptr(U),
-               int(conj), B, self._size(), D * D if nb > 1 else 0, self._stream())
+        inner = self._stride(axis)
+        self._pass("gate1/axis%d" % (naxes - 1 - pos), "b200_apply_gate1", _ptr(self._buf),
+                   self._size() // (D * inner), D, inner, _ptr(U),
+                   int(conj), B, self._size(), D * D if nb > 1 else 0, self._stream())
 
     def _k_gate2(self, G, rule, ax1, ax2, conj):
         self._own()
@@ -867,6 +869,17 @@ class DeviceCircuit:
         fid = np.abs(v) ** 2 if self._pure else v
         res = np.abs(fid - 1) <= tol
         return res if self._batched else bool(res[0])
+
+    def element(self, n):
+        """<n|psi> (pure) or <n|rho|n> (mixed) for the Fock indices ``n``, one value per batch
+        entry (states.py:644-655): a D2H read of B numbers, whatever the physical axis order."""
+        self._flush()
+        per = self._size()
+        if self._pure:
+            idx = sum(int(x) * self._stride(i) for i, x in enumerate(n))
+        else:
+            idx = sum(int(x) * (self._stride(2 * i) + self._stride(2 * i + 1)) for i, x in enumerate(n))
+        return self._buf[idx::per].cpu().numpy()
 
     def get_state(self):
         """(device tensor snapshot, pure) -- the reference returns its live array

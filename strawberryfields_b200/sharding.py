@@ -1,0 +1,305 @@
+"""Pure states sharded over several GPUs (one process per GPU, ``torch.distributed``).
+
+The reference has no distributed path; this is the scale-out row of
+the hot-path scope table (section 8e): a D^n state that does not fit, or should not sit,
+on one GPU is cut along its LEADING tensor axes.
+
+Layout.  The world size P is factored as p_0 * p_1 * ... * p_{g-1} with every p_k a divisor
+of the cutoff D (D = 10: P = 2, 4, 8 -> (2), (2,2), (2,2,2)).  Physical axis k < g is split
+as i_k = b_k * (D / p_k) + j_k; the digits (b_0 .. b_{g-1}) are the rank, so every rank
+holds the tensor [D/p_0, .., D/p_{g-1}, D, .., D].  Axes g .. n-1 are whole on every rank:
+a gate on modes stored there is a purely local launch of the single-GPU kernels.
+
+Exchange.  A gate on a mode stored on a sharded axis first swaps ALL g sharded axes with g
+local ones in one all-to-all (each rank keeps 1/P of its shard and sends (P-1)/P of it --
+cheaper per mode than g pairwise half-shard swaps): pack (strided gather) ->
+``all_to_all_single`` (NCCL over NVLink / NVSwitch) -> unpack (strided gather).  Which
+logical mode lives on which physical axis is tracked on the host; nothing is swapped back.
+
+Scheduling.  Gates are queued (as in the single-GPU lazy queue) and, at a flush, executed
+in dependency order preferring gates whose modes are local; when every runnable gate needs
+a sharded mode the exchange brings those modes in and evicts the local modes whose next
+use is farthest away (Belady), so a rectangular interferometer mesh needs only a handful of
+exchanges.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import lib as L
+from . import scheduler as S
+from .circuit import DeviceCircuit, _ptr
+
+
+def factor_world(P, D):
+    """P = p_0 * ... * p_{g-1}, each p_k a divisor of D (largest divisors first)."""
+    ps, rem = [], P
+    while rem > 1:
+        cand = [d for d in range(2, D + 1) if D % d == 0 and rem % d == 0]
+        if not cand:
+            raise ValueError("world size %d cannot be factored into divisors of the cutoff %d" % (P, D))
+        ps.append(max(cand))
+        rem //= ps[-1]
+    return ps
+
+
+class ShardedCircuit(DeviceCircuit):
+    """``DeviceCircuit`` whose pure state is sharded over the ranks of a process group."""
+
+    def __init__(self, num, trunc, group=None, **opts):
+        if not dist.is_available() or not dist.is_initialized():
+            raise L.B200Error("ShardedCircuit needs an initialised torch.distributed process group")
+        self._pg = group
+        self._rank = dist.get_rank(group)
+        self._world = dist.get_world_size(group)
+        self._ps = factor_world(self._world, trunc)
+        self._g = len(self._ps)
+        if self._g > num - 1:
+            raise ValueError("%d modes are too few to shard over %d ranks at cutoff %d" % (num, self._world, trunc))
+        digits, r = [], self._rank
+        for p in reversed(self._ps):
+            digits.append(r % p)
+            r //= p
+        self._digits = list(reversed(digits))  # b_0 .. b_{g-1}, b_0 most significant
+        self.exchanges = 0
+        self.exchange_bytes = 0
+        opts.pop("batch_size", None)
+        opts["fuse"] = "fold"
+        super().__init__(num, trunc, pure=True, **opts)
+
+    # ------------------------------------------------------------------ geometry
+    def _ext(self, pos):
+        return self._trunc // self._ps[pos] if pos < self._g else self._trunc
+
+    def _size(self):
+        n = 1
+        for pos in range(self._num_modes):
+            n *= self._ext(pos)
+        return n
+
+    def _local_stride(self, pos):
+        s = 1
+        for q in range(pos + 1, self._num_modes):
+            s *= self._ext(q)
+        return s
+
+    def _stride(self, axis):
+        return self._local_stride(self._pos[axis])
+
+    def _canonicalize(self):  # the sharded layout is never canonical; readers go through _stride()
+        return
+
+    def _to_mixed(self):
+        raise NotImplementedError("mixed states are not sharded yet (loss / del_mode / measurement on a "
+                                  "sharded b200fock circuit)")
+
+    def reset(self, pure=None, cutoff_dim=None, num_subsystems=None):
+        if pure is False:
+            raise NotImplementedError("sharded b200fock circuits hold pure states only")
+        if num_subsystems is not None:
+            self._num_modes = num_subsystems
+        if cutoff_dim is not None:
+            if cutoff_dim != getattr(self, "_trunc", cutoff_dim):
+                self._ps = factor_world(self._world, cutoff_dim)
+                self._g = len(self._ps)
+            self._trunc = cutoff_dim
+        self._pure = True
+        self._scratch = self._send = self._recv = None
+        self._shared = False
+        self._buf = self._new(self._size())
+        L.call("b200_fill_zero", _ptr(self._buf), self._buf.numel(), self._stream())
+        if self._rank == 0:
+            L.call("b200_set_element", _ptr(self._buf), 0, 1.0, 0.0, self._stream())
+        self._pending = {}
+        self._opq = []
+        self._phys = list(range(self._num_modes))
+        self._pos = list(range(self._num_modes))
+        self._untouched = set(range(self._num_modes))
+
+    # ------------------------------------------------------------------ queue: everything is deferred
+    def _tile_mode(self):
+        return False
+
+    def _emit_dense(self, U, mode):
+        self._opq.append(S.Op(S.KIND_SINGLE, (mode,), U, 0, self._trunc ** 2))
+
+    def _emit_diags(self, items):
+        for d, mode in items:
+            self._opq.append(S.Op(S.KIND_DIAG, (mode,), d, 0, self._trunc, 0.2))
+
+    def _emit_pair(self, G, rule, m1, m2):
+        self._opq.append(S.Op(rule, (m1, m2), G, 0, L.packed_size(self._trunc)))
+
+    def cross_kerr_interaction(self, kappa, mode1, mode2):
+        raise NotImplementedError("cross_kerr_interaction on a sharded b200fock circuit")
+
+    def _exec(self, op):
+        if op.kind == S.KIND_SINGLE:
+            self._k_gate1(op.table, op.axes[0], op.conj)
+        elif op.kind == S.KIND_DIAG:
+            self._k_diag_multi([(op.table, op.axes[0])])
+        else:
+            self._k_gate2(op.table, op.kind, op.axes[0], op.axes[1], op.conj)
+
+    def _run_queue(self):
+        """Execute the queue in dependency order, local gates first, exchanging when stuck."""
+        if not self._opq:
+            return
+        ops, self._opq = self._opq, []
+        self._own()
+        g = self._g
+        order = list(range(len(ops)))
+        while order:
+            blocked, rest = set(), []
+            for i in order:
+                ax = ops[i].axes
+                if not any(a in blocked for a in ax) and all(self._pos[a] >= g for a in ax):
+                    self._exec(ops[i])
+                else:
+                    blocked.update(ax)
+                    rest.append(i)
+            order = rest
+            if not order:
+                break
+            # every runnable gate touches a sharded axis: bring all sharded modes in, evict the local
+            # modes whose next use is farthest in the remaining program (Belady)
+            next_use = {}
+            for rank_, i in enumerate(order):
+                for a in ops[i].axes:
+                    next_use.setdefault(a, rank_)
+            local = [(next_use.get(self._phys[pos], 1 << 30), pos) for pos in range(g, self._num_modes)]
+            local.sort(reverse=True)
+            self._exchange(sorted(pos for _, pos in local[:g]))
+
+    # ------------------------------------------------------------------ the exchange
+    def _contig(self, exts):
+        st, acc = [], 1
+        for e in reversed(exts):
+            st.append(acc)
+            acc *= e
+        return list(reversed(st))
+
+    def _exchange(self, T):
+        """Swap sharded axis k with local axis T[k] for every k (one all-to-all)."""
+        g, n, D = self._g, self._num_modes, self._trunc
+        assert len(T) == g and all(t >= g for t in T)
+        size = self._size()
+        if self._send is None:
+            self._send, self._recv = self._new(size), self._new(size)
+        ls = [self._local_stride(p) for p in range(n)]
+        sub = [D // p for p in self._ps]
+        # ---- pack: send[c_0..c_{g-1}][j_0..j_{g-1}][local axes, T[k] restricted to m_k] ----
+        exts, src = [], []
+        for k in range(g):
+            exts.append(self._ps[k])
+            src.append(sub[k] * ls[T[k]])
+        for k in range(g):
+            exts.append(sub[k])
+            src.append(ls[k])
+        for pos in range(g, n):
+            if pos in T:
+                exts.append(sub[T.index(pos)])
+            else:
+                exts.append(D)
+            src.append(ls[pos])
+        dstc = self._contig(exts)
+        self._gather(self._buf, None, self._send, [(e, s, 0, c) for e, s, c in zip(exts, src, dstc)])
+        # ---- all-to-all: block q of `send` goes to rank q ----
+        dist.all_to_all_single(self._recv.view(torch.float64), self._send.view(torch.float64), group=self._pg)
+        # ---- unpack: recv[b_0..b_{g-1}][j_0..][.. m_k at T[k] ..] -> new local tensor ----
+        rs = dict()  # name -> stride inside recv
+        names = [("b", k) for k in range(g)] + [("j", k) for k in range(g)] + [("l", pos) for pos in range(g, n)]
+        for nm, st in zip(names, dstc):
+            rs[nm] = st
+        oa = []
+        for pos in range(n):
+            if pos < g:
+                oa.append((sub[pos], rs[("l", T[pos])], 0, ls[pos]))       # m_k becomes the sharded remainder
+            elif pos in T:
+                k = T.index(pos)
+                oa.append((self._ps[k], rs[("b", k)], 0, sub[k] * ls[pos]))  # sender's rank digit
+                oa.append((sub[k], rs[("j", k)], 0, ls[pos]))                # sender's local remainder
+            else:
+                oa.append((D, rs[("l", pos)], 0, ls[pos]))
+        self._gather(self._recv, None, self._buf, oa)
+        phys = list(self._phys)
+        for k in range(g):
+            phys[k], phys[T[k]] = phys[T[k]], phys[k]
+        self._phys = phys
+        pos = [0] * n
+        for p, v in enumerate(phys):
+            pos[v] = p
+        self._pos = pos
+        self.exchanges += 1
+        self.exchange_bytes += 16 * size * (self._world - 1) // self._world
+
+    # ------------------------------------------------------------------ observation
+    def _norm_device(self):
+        self._flush()
+        out = torch.zeros(1, dtype=torch.float64, device=self.device)
+        L.call("b200_norm2", _ptr(self._buf), self._size(), _ptr(out), _ptr(self._norm_part), self._stream())
+        dist.all_reduce(out, group=self._pg)
+        return out
+
+    def norm(self):
+        return float(np.sqrt(self._norm_device().cpu().numpy()[0]))
+
+    def element(self, n):
+        """<n|psi>: read on the owning rank, shared with all ranks."""
+        self._flush()
+        idx, mine = 0, True
+        for mode, x in enumerate(n):
+            pos = self._pos[mode]
+            x = int(x)
+            if pos < self._g:
+                sub = self._trunc // self._ps[pos]
+                if x // sub != self._digits[pos]:
+                    mine = False
+                x = x % sub
+            idx += x * self._local_stride(pos)
+        val = torch.zeros(2, dtype=torch.float64, device=self.device)
+        if mine:
+            val = torch.view_as_real(self._buf[idx:idx + 1]).reshape(2).clone()
+        dist.all_reduce(val, group=self._pg)
+        v = val.cpu().numpy()
+        return np.array([v[0] + 1j * v[1]])
+
+    def host_state(self):
+        """The whole ket on every rank's host (small states / tests only)."""
+        self._flush()
+        g, n, D = self._g, self._num_modes, self._trunc
+        parts = [torch.empty_like(self._buf) for _ in range(self._world)]
+        dist.all_gather(parts, self._buf, group=self._pg)
+        full = torch.stack(parts).cpu().numpy()
+        local_ext = [self._ext(p) for p in range(n)]
+        full = full.reshape(self._ps + local_ext)  # [b_0..b_{g-1}, j_0..j_{g-1}, local...]
+        order = []
+        for k in range(g):
+            order += [k, g + k]
+        order += list(range(2 * g, g + n))
+        full = full.transpose(order).reshape([D] * n)  # physical axis order
+        return np.ascontiguousarray(full.transpose([self._pos[m] for m in range(n)]))
+
+    def is_vacuum(self, tol):
+        v = self.element([0] * self._num_modes)[0]
+        return bool(np.abs(np.abs(v) ** 2 - 1) <= tol)
+
+    def snapshot(self):
+        self._flush()
+        snap = object.__new__(ShardedCircuit)
+        snap.__dict__.update(self.__dict__)
+        snap._pending, snap._opq, snap._untouched = {}, [], set()
+        snap._scratch = snap._send = snap._recv = snap._part = None
+        snap._norm_part = torch.zeros(4096, dtype=torch.float64, device=self.device)
+        snap._shared = True
+        self._shared = True
+        return snap
+
+    # ------------------------------------------------------------------ not sharded yet
+    def _unsupported(self, *a, **k):
+        raise NotImplementedError("this operation is not available on a sharded b200fock circuit yet")
+
+    prepare_multimode = alloc = dealloc = measure_fock = measure_homodyne = _unsupported
+    marginal_probs_device = reduced_dm_device = fock_probs_device = _unsupported

@@ -102,14 +102,7 @@ class _FockStateMixin:
             raise ValueError("List length should be equal to number of modes")
         if max(n) >= self._cutoff:
             raise ValueError("Can't get distribution beyond truncation level")
-        v = self._view
-        v._flush()
-        per = v._size()
-        if self._pure:
-            idx = sum(int(x) * v._stride(i) for i, x in enumerate(n))
-        else:
-            idx = sum(int(x) * (v._stride(2 * i) + v._stride(2 * i + 1)) for i, x in enumerate(n))
-        vals = v._buf[idx::per].cpu().numpy()
+        vals = self._view.element(n)
         res = np.abs(vals) ** 2 if self._pure else vals.real
         return res if self._batched else res[0]
 

@@ -1,0 +1,62 @@
+"""Worker of tests/test_sharding.py: run under torchrun with the gloo backend.  Each rank
+drives a ShardedCircuit (host logic + numpy double of the C ABI) through a circuit and
+checks the gathered ket against the single-process oracle."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    mode = sys.argv[1]          # "host" (gloo + numpy double) or "gpu" (nccl + CUDA kernels)
+    n, D = int(sys.argv[2]), int(sys.argv[3])
+    from strawberryfields_b200 import circuit, lib
+    from strawberryfields_b200 import workloads as W
+    from strawberryfields_b200.backend import B200FockBackend
+
+    if mode == "host":
+        from fake_lib import FakeLib
+
+        lib._lib = FakeLib()
+        circuit._TEST_HOST_MODE = True
+        dist.init_process_group("gloo")
+    else:
+        import torch
+
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl")
+    from oracle.fock_oracle import OracleBackend
+
+    calls = W.config2_circuit(n, seed=5)
+    extra = [("mzgate", 0.4, 1.1, 0, n - 1), ("two_mode_squeeze", 0.2, 0.3, n - 1, 1), ("kerr_interaction", 0.1, 0),
+             ("beamsplitter", 0.7, 0.2, 1, 0)]
+    be = B200FockBackend()
+    be.begin_circuit(n, cutoff_dim=D, shard=True)
+    W.run_calls(be, calls + extra)
+    st = be.state()
+    ket = st.ket()
+    ob = OracleBackend()
+    ob.begin_circuit(n, cutoff_dim=D)
+    W.run_calls(ob, calls + extra)
+    want = ob.state().data
+    err = float(np.abs(ket - want).max())
+    tr_err = abs(st.trace() - np.vdot(want, want).real)
+    idx = [1] + [0] * (n - 2) + [2 % D]
+    fp_err = abs(st.fock_prob(idx) - np.abs(want[tuple(idx)]) ** 2)
+    ok = bool(err < 1e-12 and tr_err < 1e-12 and fp_err < 1e-12)
+    print(json.dumps({"rank": dist.get_rank(), "world": dist.get_world_size(), "err": err,
+                      "trace_err": float(tr_err), "fock_prob_err": float(fp_err),
+                      "exchanges": int(be.circuit.exchanges), "ok": ok}))
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()

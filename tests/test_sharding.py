@@ -1,0 +1,62 @@
+"""Sharded states: world_size-2 and -4 runs on the CPU with the gloo backend,
+driving the host logic (rank/axis geometry, exchange planning, pack / all-to-all / unpack)
+against the numpy double of the C ABI; the gathered ket must equal the oracle's to 1e-12.
+The same worker runs on GPUs with NCCL (``-m gpu``, needs >= 2 devices)."""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _run(mode, world, n, D):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+           os.path.join(ROOT, "tests", "dist_worker.py"), mode, str(n), str(D)]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    import re
+
+    lines = [json.loads(m) for m in re.findall(r"\{[^{}]*\}", res.stdout)]  # ranks may share a line
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert len(lines) == world and all(l["ok"] for l in lines), lines
+    return lines
+
+
+def test_factor_world():
+    from strawberryfields_b200.sharding import factor_world
+
+    assert factor_world(2, 10) == [2]
+    assert factor_world(4, 10) == [2, 2]
+    assert factor_world(8, 10) == [2, 2, 2]
+    assert factor_world(6, 6) == [6]
+    assert factor_world(4, 6) == [2, 2]
+    with pytest.raises(ValueError):
+        factor_world(2, 7)
+
+
+@pytest.mark.parametrize("world,n,D", [(2, 4, 4), (4, 5, 4), (3, 4, 6)])
+def test_sharded_circuit_matches_oracle_gloo(world, n, D):
+    lines = _run("host", world, n, D)
+    assert lines[0]["exchanges"] >= 1  # the circuit touches sharded modes: at least one all-to-all
+
+
+@pytest.mark.gpu
+def test_sharded_circuit_matches_oracle_nccl():
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 2 if torch.cuda.device_count() < 4 else 4
+    _run("gpu", world, 5, 6)
