@@ -167,10 +167,15 @@ def b200_arm(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     handle = lib.load(build_if_missing=False)
 
-    n_modes, D = args.modes, args.cutoff
-    calls = W.config2_circuit(n_modes, seed=42 + rank)
-    elements = D ** n_modes
+    # N = 1: BASELINE config 2 (8 modes).  N > 1: BASELINE config 5 -- ONE 9-mode state sharded over
+    # the N GPUs (strong scaling), gates on sharded modes served by the all-to-all axis exchange.
+    sharded = world > 1
+    n_modes, D = (args.modes if args.modes else (9 if sharded else 8)), args.cutoff
+    calls = W.config2_circuit(n_modes, seed=42)
+    elements = D ** n_modes                    # whole-job amplitudes
+    local_elements = elements // world if sharded else elements
     updates_per_step = len(calls) * elements
+    shard_kw = {"shard": True} if sharded else {}
 
     def barrier():
         if world > 1:
@@ -180,7 +185,7 @@ def b200_arm(args):
     # ---- device-resident leg: `value` ---------------------------------------------------
     fuse = {"tile": "tile", "fold": "fold", "off": False}[args.fuse]
     be = B200FockBackend()
-    be.begin_circuit(n_modes, cutoff_dim=D, fuse=fuse)
+    be.begin_circuit(n_modes, cutoff_dim=D, fuse=fuse, **shard_kw)
     for _ in range(args.warmup):
         W.run_calls(be, calls)
         be.circuit._flush()
@@ -201,7 +206,8 @@ def b200_arm(args):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
-    value = updates_per_step * args.steps * world / (ms_total * 1e-3)
+    value = updates_per_step * args.steps / (ms_total * 1e-3)   # whole job: one state, all GPUs
+    exchanges = getattr(be.circuit, "exchanges", 0)
 
     # ---- roofline leg: per-launch CUDA events on one more step ------------------------------
     prof = []
@@ -212,6 +218,8 @@ def b200_arm(args):
     be.circuit.profile = None
     by_tag = {}
     for tag, nbytes, a, b in prof:
+        if tag == "exchange":  # reported separately (NVLink, not HBM)
+            continue
         t = a.elapsed_time(b) * 1e-3
         d = by_tag.setdefault(tag, [0, 0.0, 0])
         d[0] += nbytes
@@ -232,7 +240,7 @@ def b200_arm(args):
         "share_of_step_time": dom_time / max(sum(g[1] for g in groups.values()), 1e-12),
         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
         "launches_per_step": dom_n, "avg_launch_ms": dom_time / max(dom_n, 1) * 1e3,
-        "algorithmic_bytes_per_launch": 32 * elements,
+        "algorithmic_bytes_per_launch": 32 * local_elements,
         "frac_of_nominal_8TBs": achieved / 8000.0,
         "by_pass": {tag: {"launches": v[2], "GBps": v[0] / v[1] / 1e9} for tag, v in sorted(by_tag.items())},
     }
@@ -259,7 +267,7 @@ def b200_arm(args):
     def e2e_step():
         dev_params = pinned.to("cuda", non_blocking=True)  # H2D of the step's inputs
         be2 = B200FockBackend()
-        be2.begin_circuit(n_modes, cutoff_dim=D, fuse=fuse)
+        be2.begin_circuit(n_modes, cutoff_dim=D, fuse=fuse, **shard_kw)
         for i, c in enumerate(calls):
             modes = [x for x in c[1:] if isinstance(x, int)]
             getattr(be2, c[0])(*([DeviceParams(dev_params[i])] + ([None] if c[0] != "rotation" else []) + modes))
@@ -279,7 +287,7 @@ def b200_arm(args):
     ms2 = torch.tensor([max(e0.elapsed_time(e1), wall * 1e3)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-    e2e_value = updates_per_step * args.steps * world / (float(ms2.item()) * 1e-3)
+    e2e_value = updates_per_step * args.steps / (float(ms2.item()) * 1e-3)
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(ptab.nbytes),
            "d2h_bytes_per_step": int(8 * (len(outcomes) + 1)),
            "api": "B200FockBackend.begin_circuit/gates/state().trace()/fock_prob()"}
@@ -297,21 +305,34 @@ def b200_arm(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "complex128", "data": "synthetic",
+            "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "complex128",
+            "data": "synthetic",
             "config": {
-                "workload": "BASELINE config 2: %d-mode pure state, cutoff %d (%.3g complex128 amplitudes), "
+                "workload": "BASELINE config %s: %d-mode pure state, cutoff %d (%.3g complex128 amplitudes), "
                             "Sgate+Dgate per mode + random rectangular interferometer, %d gates per step"
-                            % (n_modes, D, elements, len(calls)),
-                "parallelism": "replicas x%d" % world if world > 1 else "single GPU",
-                "l2": "state %.2f GB per GPU > 126 MB L2: every pass streams from HBM" % (elements * 16 / 1e9),
+                            % ("5 (one state sharded over %d GPUs)" % world if sharded else "2", n_modes, D,
+                               elements, len(calls)),
+                "parallelism": ("state sharded on its leading axes over %d ranks, NCCL all-to-all axis exchange"
+                                % world) if sharded else "single GPU",
+                "l2": "state %.2f GB per GPU > 126 MB L2: every pass streams from HBM"
+                      % (local_elements * 16 / 1e9),
                 "passes_per_step": sum(v[2] for v in by_tag.values()),
                 "gate_queue": args.fuse,
             },
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
-            "hbm_GBps_whole_step": 32 * elements * sum(v[2] for v in by_tag.values()) * args.steps
-                                   / (ms_total * 1e-3) / 1e9,
+            "hbm_GBps_per_gpu_whole_step": 32 * local_elements * sum(v[2] for v in by_tag.values()) * args.steps
+                                           / (ms_total * 1e-3) / 1e9,
             "circuit_ms": ms_total / args.steps,
         }
+        if sharded:
+            ex = [(nb, a.elapsed_time(b) * 1e-3) for tag, nb, a, b in prof if tag == "exchange"]
+            line["exchange"] = {
+                "all_to_all_per_step": len(ex),
+                "bytes_sent_per_gpu_per_exchange": int(16 * local_elements * (world - 1) // world),
+                "GBps_per_gpu_per_direction_incl_pack_unpack":
+                    (sum(nb for nb, _ in ex) / sum(t for _, t in ex) / 1e9) if ex else None,
+                "exchanges_in_timed_region": int(exchanges),
+            }
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))
@@ -325,7 +346,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--modes", type=int, default=8)
+    ap.add_argument("--modes", type=int, default=0, help="default: 8 on one GPU, 9 sharded")
     ap.add_argument("--cutoff", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fuse", default="fold", choices=["tile", "fold", "off"],

@@ -188,6 +188,10 @@ class ShardedCircuit(DeviceCircuit):
         size = self._size()
         if self._send is None:
             self._send, self._recv = self._new(size), self._new(size)
+        prof = self.__dict__.get("profile")
+        if prof is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
         ls = [self._local_stride(p) for p in range(n)]
         sub = [D // p for p in self._ps]
         # ---- pack: send[c_0..c_{g-1}][j_0..j_{g-1}][local axes, T[k] restricted to m_k] ----
@@ -224,6 +228,9 @@ class ShardedCircuit(DeviceCircuit):
             else:
                 oa.append((D, rs[("l", pos)], 0, ls[pos]))
         self._gather(self._recv, None, self._buf, oa)
+        if prof is not None:
+            ev1.record()
+            prof.append(("exchange", 16 * size * (self._world - 1) // self._world, ev0, ev1))
         phys = list(self._phys)
         for k in range(g):
             phys[k], phys[T[k]] = phys[T[k]], phys[k]
