@@ -169,9 +169,12 @@ class ShardedCircuit(DeviceCircuit):
             for rank_, i in enumerate(order):
                 for a in ops[i].axes:
                     next_use.setdefault(a, rank_)
-            local = [(next_use.get(self._phys[pos], 1 << 30), pos) for pos in range(g, self._num_modes)]
+            # ties: keep the two innermost axes for the residents -- the modes coming in are used at
+            # once, and the streaming kernels are slowest on the last two axes
+            n = self._num_modes
+            local = [(next_use.get(self._phys[pos], 1 << 30), pos < n - 2, pos) for pos in range(g, n)]
             local.sort(reverse=True)
-            self._exchange(sorted(pos for _, pos in local[:g]))
+            self._exchange(sorted(pos for _, _, pos in local[:g]))
 
     # ------------------------------------------------------------------ the exchange
     def _contig(self, exts):
