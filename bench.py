@@ -170,12 +170,28 @@ def b200_arm(args):
     # N = 1: BASELINE config 2 (8 modes).  N > 1: BASELINE config 5 -- ONE 9-mode state sharded over
     # the N GPUs (strong scaling), gates on sharded modes served by the all-to-all axis exchange.
     sharded = world > 1
-    n_modes, D = (args.modes if args.modes else (9 if sharded else 8)), args.cutoff
-    calls = W.config2_circuit(n_modes, seed=42)
-    elements = D ** n_modes                    # whole-job amplitudes
+    D = args.cutoff
+    shard_kw = {"shard": True} if sharded else {}
+    if args.workload == "c3":      # BASELINE config 3: 4-mode MIXED state, S/BS layers + LossChannel(0.9)
+        n_modes = args.modes or 4
+        calls = W.config3_circuit(n_modes, seed=42)
+        elements = D ** (2 * n_modes)
+        shard_kw = {"pure": False}
+        wl_name = "3: %d-mode mixed state (density matrix), Sgate/BSgate layers + LossChannel(0.9) per mode" % n_modes
+    elif args.workload == "c4":    # BASELINE config 4: QNN layer, 6 modes, batch of 64 pure states
+        n_modes = args.modes or 6
+        calls = W.config4_circuit(n_modes, batch=args.batch, seed=42)
+        elements = args.batch * D ** n_modes
+        shard_kw = {"batch_size": args.batch}
+        wl_name = "4: CV-QNN layer, %d modes, batch of %d pure states, per-entry weights" % (n_modes, args.batch)
+    else:
+        n_modes = args.modes or (9 if sharded else 8)
+        calls = W.config2_circuit(n_modes, seed=42)
+        elements = D ** n_modes                    # whole-job amplitudes
+        wl_name = ("5 (one state sharded over %d GPUs)" % world if sharded else "2") + \
+            ": %d-mode pure state, Sgate+Dgate per mode + random rectangular interferometer" % n_modes
     local_elements = elements // world if sharded else elements
     updates_per_step = len(calls) * elements
-    shard_kw = {"shard": True} if sharded else {}
 
     def barrier():
         if world > 1:
@@ -251,11 +267,16 @@ def b200_arm(args):
     # read back to the host.
     from strawberryfields_b200 import DeviceParams
 
-    def params_of(c):
-        vals = [float(x) for x in c[1:] if isinstance(x, float)]
-        return (vals + [0.0, 0.0])[:2]
+    nb = args.batch if args.workload == "c4" else 1
+    two_param = ("squeeze", "displacement", "beamsplitter", "mzgate", "two_mode_squeeze")
 
-    ptab = np.array([params_of(c) for c in calls], dtype=np.float64)
+    def params_of(c):  # -> [2, nb]
+        vals = [np.broadcast_to(np.asarray(x, dtype=np.float64), (nb,)) for x in c[1:]
+                if not isinstance(x, (int, np.integer))]
+        vals += [np.zeros(nb)] * (2 - len(vals))
+        return np.stack(vals[:2])
+
+    ptab = np.ascontiguousarray(np.stack([params_of(c) for c in calls]))  # [ncalls, 2, nb]
     pinned = torch.from_numpy(ptab).pin_memory()
     outcomes = [[0] * n_modes]
     for m in range(n_modes):
@@ -269,8 +290,8 @@ def b200_arm(args):
         be2 = B200FockBackend()
         be2.begin_circuit(n_modes, cutoff_dim=D, fuse=fuse, **shard_kw)
         for i, c in enumerate(calls):
-            modes = [x for x in c[1:] if isinstance(x, int)]
-            getattr(be2, c[0])(*([DeviceParams(dev_params[i])] + ([None] if c[0] != "rotation" else []) + modes))
+            modes = [x for x in c[1:] if isinstance(x, (int, np.integer))]
+            getattr(be2, c[0])(*([DeviceParams(dev_params[i])] + ([None] if c[0] in two_param else []) + modes))
         st = be2.state()
         return np.array([st.trace()] + [st.fock_prob(o) for o in outcomes])  # D2H reads
 
@@ -289,7 +310,7 @@ def b200_arm(args):
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e_value = updates_per_step * args.steps / (float(ms2.item()) * 1e-3)
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(ptab.nbytes),
-           "d2h_bytes_per_step": int(8 * (len(outcomes) + 1)),
+           "d2h_bytes_per_step": int(8 * (len(outcomes) + 1) * nb),
            "api": "B200FockBackend.begin_circuit/gates/state().trace()/fock_prob()"}
 
     # ---- CPU baseline (rank 0, N = 1 only) -----------------------------------------------------
@@ -308,10 +329,8 @@ def b200_arm(args):
             "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "complex128",
             "data": "synthetic",
             "config": {
-                "workload": "BASELINE config %s: %d-mode pure state, cutoff %d (%.3g complex128 amplitudes), "
-                            "Sgate+Dgate per mode + random rectangular interferometer, %d gates per step"
-                            % ("5 (one state sharded over %d GPUs)" % world if sharded else "2", n_modes, D,
-                               elements, len(calls)),
+                "workload": "BASELINE config %s; cutoff %d, %.3g stored complex128 elements, %d gates per step"
+                            % (wl_name, D, elements, len(calls)),
                 "parallelism": ("state sharded on its leading axes over %d ranks, NCCL all-to-all axis exchange"
                                 % world) if sharded else "single GPU",
                 "l2": "state %.2f GB per GPU > 126 MB L2: every pass streams from HBM"
@@ -349,6 +368,9 @@ def main():
     ap.add_argument("--modes", type=int, default=0, help="default: 8 on one GPU, 9 sharded")
     ap.add_argument("--cutoff", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"],
+                    help="c2 (default; c5 when sharded over N > 1 GPUs), c3 = mixed state + loss, c4 = batched QNN layer")
+    ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--fuse", default="fold", choices=["tile", "fold", "off"],
                     help="gate queue: tile passes (default), diagonal folding only, or one pass per gate")
     args = ap.parse_args()

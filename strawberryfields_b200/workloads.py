@@ -114,7 +114,6 @@ def config4_circuit(N=6, batch=64, seed=42):
     calls += interferometer()
     for m in range(N):
         calls.append(("displacement", np.abs(rng.normal(0, 0.05, batch)), rng.uniform(0, 2 * np.pi, batch), m))
-    for m in range(N):
         calls.append(("kerr_interaction", rng.normal(0, 0.05, batch), m))
     return calls
 

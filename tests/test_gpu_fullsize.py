@@ -1,0 +1,168 @@
+"""BASELINE-size checks on the GPU through size-independent properties (the oracle cannot hold
+1e8-1e9 amplitudes in seconds): analytic single-photon transfer through the interferometer
+mesh, exact norm conservation of passive circuits on few-photon inputs, linearity, agreement
+of the three gate-queue modes, trace preservation and Hermiticity under the loss channel,
+and oracle comparisons on sampled batch entries.  Tolerance 1e-12 unless stated."""
+import numpy as np
+import pytest
+
+from strawberryfields_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def _backend(**kw):
+    from strawberryfields_b200 import B200FockBackend
+
+    be = B200FockBackend()
+    n = kw.pop("n")
+    be.begin_circuit(n, **kw)
+    return be
+
+
+def _single_photon_check(n, D, fuse):
+    """|1_k> through a passive mesh: <1_j|psi> = U[j, k] -- analytic at any size."""
+    rng = np.random.RandomState(7)
+    calls = W.interferometer_calls(n, rng)
+    U = W.interferometer_unitary(n, calls)
+    k = n // 2
+    be = _backend(n=n, cutoff_dim=D, fuse=fuse)
+    be.prepare_fock_state(1, k)
+    W.run_calls(be, calls)
+    st = be.state()
+    assert st.is_pure
+    for j in range(n):
+        idx = [0] * n
+        idx[j] = 1
+        amp = st._view.element(idx)[0]
+        assert abs(amp - U[j, k]) < TOL, (j, amp, U[j, k])
+    assert abs(st.trace() - 1.0) < 1e-11
+
+
+@pytest.mark.parametrize("fuse", [True, "tile"])
+def test_config2_size_single_photon_transfer(fuse):
+    _single_photon_check(8, 10, fuse)  # 1e8 amplitudes, 64-gate mesh
+
+
+def test_config5_size_single_photon_transfer():
+    _single_photon_check(9, 10, True)  # 1e9 amplitudes (16 GB)
+
+
+def test_config2_size_passive_norm_and_round_trip():
+    """Photon number is conserved by R / BS: with 3 photons < cutoff the truncated mesh is exactly
+    unitary on the input, so the norm stays 1 and the inverse mesh returns |1,1,0,1,0,..>."""
+    n, D = 8, 10
+    rng = np.random.RandomState(3)
+    calls = W.interferometer_calls(n, rng)
+    inverse = []
+    for c in reversed(calls):
+        if c[0] == "rotation":
+            inverse.append(("rotation", -c[1], c[2]))
+        else:
+            inverse.append(("beamsplitter", -c[1], c[2], c[3], c[4]))
+    be = _backend(n=n, cutoff_dim=D)
+    for m, k in enumerate([1, 1, 0, 1, 0, 0, 0, 0]):
+        be.prepare_fock_state(k, m)
+    W.run_calls(be, calls)
+    assert abs(be.state().trace() - 1.0) < 1e-11
+    W.run_calls(be, inverse)
+    st = be.state()
+    assert abs(st.fock_prob([1, 1, 0, 1, 0, 0, 0, 0]) - 1.0) < 1e-11
+
+
+def test_config2_size_queue_modes_agree_and_linearity():
+    import torch
+
+    n, D = 8, 10
+    calls = W.config2_circuit(n, seed=42)
+    kets = {}
+    for fuse in (True, "tile", False):
+        be = _backend(n=n, cutoff_dim=D, fuse=fuse)
+        W.run_calls(be, calls)
+        be.circuit._flush()
+        be.circuit._canonicalize()
+        kets[fuse] = be.circuit._buf.clone()
+    ref = kets[False]
+    for fuse in (True, "tile"):
+        assert float((kets[fuse] - ref).abs().max()) < TOL
+    # linearity on a smaller register (three resident 1.6 GB states would also fit; 7 modes keep it quick)
+    n = 7
+    rs = np.random.RandomState(1)
+    a, b = 0.6 - 0.3j, -0.2 + 0.7j
+    psi1 = rs.randn(D ** n) + 1j * rs.randn(D ** n)
+    psi2 = rs.randn(D ** n) + 1j * rs.randn(D ** n)
+    psi1 /= np.linalg.norm(psi1)
+    psi2 /= np.linalg.norm(psi2)
+    calls = W.config2_circuit(n, seed=9)
+    outs = []
+    for vec in (psi1, psi2, a * psi1 + b * psi2):
+        be = _backend(n=n, cutoff_dim=D)
+        be.prepare_ket_state(vec, list(range(n)))
+        W.run_calls(be, calls)
+        be.circuit._flush()
+        outs.append(be.circuit._buf.clone())
+    assert float((outs[2] - (a * outs[0] + b * outs[1])).abs().max()) < TOL
+    del outs, kets
+    torch.cuda.empty_cache()
+
+
+def test_config3_size_mixed_loss_measure():
+    """4-mode mixed state, cutoff 10 (1e8-element density matrix): the loss superoperator is
+    trace preserving and keeps rho Hermitian; T = 1 is the identity; the Fock marginal sums to
+    the trace; a seeded MeasureFock is reproducible and leaves the measured modes in vacuum."""
+    import torch
+
+    n, D = 4, 10
+    calls = W.config3_circuit(n, seed=42)
+    gates = [c for c in calls if c[0] != "loss"]
+    be = _backend(n=n, cutoff_dim=D, pure=False)
+    W.run_calls(be, gates)
+    tr0 = be.state().trace()
+    be.loss(1.0, 2)
+    assert abs(be.state().trace() - tr0) < TOL
+    before = be.circuit.get_state()[0]
+    be.loss(1.0, 0)
+    assert float((be.circuit.get_state()[0] - before).abs().max()) < TOL
+    del before
+    for m in range(n):
+        be.loss(0.9, m)
+    st = be.state()
+    assert abs(st.trace() - tr0) < 1e-11
+    probs = st.all_fock_probs()
+    assert abs(probs.sum() - tr0) < 1e-10 and probs.min() > -1e-12
+    # Hermiticity on the device: rho[(k),(b)] == conj(rho[(b),(k)])
+    rho = be.circuit.get_state()[0].view([D] * (2 * n))
+    perm = [x for i in range(n) for x in (2 * i + 1, 2 * i)]
+    assert float((rho - rho.permute(perm).conj()).abs().max()) < TOL
+    del rho
+    torch.cuda.empty_cache()
+    outcomes = []
+    for _ in range(2):
+        b2 = _backend(n=n, cutoff_dim=D, pure=False)
+        W.run_calls(b2, calls)
+        np.random.seed(7)
+        outcomes.append(b2.measure_fock(list(range(n))).tolist())
+        assert b2.is_vacuum(1e-10)
+        del b2
+    assert outcomes[0] == outcomes[1]
+
+
+def test_config4_size_batched_layer_vs_oracle():
+    """6 modes, cutoff 10, batch 64 (6.4e7 amplitudes): sampled batch entries equal independent
+    oracle runs with that entry's weights (the reference has no batch axis)."""
+    from oracle.fock_oracle import OracleBackend
+
+    n, D, B = 6, 10, 64
+    calls = W.config4_circuit(n, batch=B, seed=42)
+    be = _backend(n=n, cutoff_dim=D, batch_size=B)
+    W.run_calls(be, calls)
+    kets = be.state().ket()
+    assert kets.shape == (B,) + (D,) * n
+    for b in (0, 37):
+        ob = OracleBackend()
+        ob.begin_circuit(n, cutoff_dim=D)
+        for c in calls:
+            args = [x[b] if isinstance(x, np.ndarray) else x for x in c[1:]]
+            getattr(ob, c[0])(*args)
+        assert np.abs(kets[b] - ob.state().data).max() < TOL
