@@ -115,6 +115,87 @@ k_apply_blocks(cplx* __restrict__ state, const cplx* __restrict__ coef, const Ge
   }
 }
 
+// ---- gates that touch the INNERMOST axis: staged through shared memory ----------------------
+// When a gate axis has stride 1, consecutive slices are D (one-mode gate) or D*stride apart, so
+// the lanes of a warp cannot read neighbouring 16-byte words and the streaming kernel drops to
+// 3-4.6 TB/s.  Here a CTA copies the slices it owns -- whole runs of D consecutive amplitudes --
+// into shared memory with cp.async (coalesced), runs the same register-blocked tasks on the
+// staged copy (slice stride padded to an odd number of 16-byte words: conflict-free LDS.128 with
+// lanes over slices), and writes the runs back.
+__device__ __forceinline__ void cp_async16_(void* smem, const void* gmem) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+}
+
+__host__ __device__ constexpr int inner_threads(int D) { return 32 * (D < 4 ? 4 : D); }
+
+template <int D>
+__global__ void __launch_bounds__(inner_threads(D), (D <= 10 ? 3 : (D <= 12 ? 2 : 1)))
+k_apply_inner(cplx* __restrict__ state, const cplx* __restrict__ coef, const Geometry g, const TaskTable tt,
+              int rows /* D: pair gate, 1: one-mode gate */, int slices_per_cta) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* M = reinterpret_cast<cplx*>(smem_raw);
+  cplx* tile = M + g.coef_count;
+  const int nthr = inner_threads(D), tid = threadIdx.x;
+  const int batch = blockIdx.z;
+  const int SL = (rows * D) | 1;  // padded slice stride
+  const long long row_stride = g.stride1 > g.stride2 ? g.stride1 : g.stride2;  // outer gate axis (pair)
+  cplx* base = state + (size_t)batch * g.state_batch_stride;
+  const unsigned s0 = blockIdx.x * (unsigned)slices_per_cta;
+
+  // stage: a thread owns (slice, l) and walks the rows of that slice
+  for (int idx = tid; idx < slices_per_cta * D; idx += nthr) {
+    const int sg = idx / D, l = idx - sg * D;
+    const unsigned s = s0 + sg;
+    if (s < g.n_slices) {
+      const unsigned i_mid = s % g.mid, i_out = s / g.mid;
+      const cplx* src = base + (long long)i_out * g.outer_step + (long long)i_mid * g.mid_step + l;
+      cplx* dst = tile + sg * SL + l;
+      for (int k = 0; k < rows; ++k) cp_async16_(dst + k * D, src + (long long)k * row_stride);
+    }
+  }
+  {
+    const cplx* cgp = coef + (size_t)batch * g.coef_batch_stride;
+    for (int i = tid; i < g.coef_count; i += nthr) {
+      cplx v = cgp[i];
+      if (g.conj) v.y = -v.y;
+      M[i] = v;
+    }
+  }
+  asm volatile("cp.async.wait_all;\n" ::: "memory");
+  __syncthreads();
+
+  // compute on the staged copy: lanes over slices, warps over (lane group, task)
+  const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
+  const int sk = rows == 1 ? 1 : (g.stride1 > g.stride2 ? D : 1);  // staged stride of gate index 1
+  const int sl = rows == 1 ? 0 : (g.stride1 > g.stride2 ? 1 : D);  // staged stride of gate index 2
+  const long long step = sk + tt.dl * sl;
+  const int ngroups = slices_per_cta / 32;
+  for (int wt = warp; wt < ngroups * tt.ntasks; wt += nwarps) {
+    const int gi = wt / tt.ntasks, task = wt - gi * tt.ntasks;
+    const int sg = gi * 32 + lane;
+    if (s0 + sg < g.n_slices) {
+      cplx* ps = tile + sg * SL;
+      const SubBlock sb0 = tt.sub[task][0], sb1 = tt.sub[task][1];
+      task_dispatch<D>(sb0.c, ps + sb0.start_k * sk + sb0.start_l * sl, ps + sb1.start_k * sk + sb1.start_l * sl,
+                       step, M + sb0.coef, M + sb1.coef);
+    }
+  }
+  __syncthreads();
+
+  // write back the runs
+  for (int idx = tid; idx < slices_per_cta * D; idx += nthr) {
+    const int sg = idx / D, l = idx - sg * D;
+    const unsigned s = s0 + sg;
+    if (s < g.n_slices) {
+      const unsigned i_mid = s % g.mid, i_out = s / g.mid;
+      cplx* dst = base + (long long)i_out * g.outer_step + (long long)i_mid * g.mid_step + l;
+      const cplx* src = tile + sg * SL + l;
+      for (int k = 0; k < rows; ++k) dst[(long long)k * row_stride] = src[k * D];
+    }
+  }
+}
+
 // ---- diagonal gates ---------------------------------------------------------------------
 // Index arithmetic is 32-bit whenever the state has fewer than 2^32 elements (always true for
 // one launch on one GPU: 180 GB / 16 B = 1.1e10 would need it, 1e9-1e10-element shards do not).
@@ -191,8 +272,41 @@ static cudaError_t launch_blocks_d(cplx* state, const cplx* coef, const Geometry
   return cudaSuccess;
 }
 
+template <int D>
+static cudaError_t launch_inner_d(cplx* state, const cplx* coef, const Geometry& g, const TaskTable& tt, int rows,
+                                  int nbatch, cudaStream_t st) {
+  const int spc = rows == 1 ? inner_threads(D) : 32;  // slices per CTA: one per thread / one lane group
+  const int SL = (rows * D) | 1;
+  size_t smem = ((size_t)g.coef_count + (size_t)spc * SL) * sizeof(cplx);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k_apply_inner<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  dim3 grid((g.n_slices + spc - 1) / spc, 1, nbatch);
+  k_apply_inner<D><<<grid, inner_threads(D), smem, st>>>(state, coef, g, tt, rows, spc);
+  return cudaSuccess;
+}
+
 static int launch_blocks(int D, cplx* state, const cplx* coef, Geometry& g, const TaskTable& tt, int nbatch,
                          cudaStream_t st) {
+  if (g.inner == 1 && D >= 2 && D <= B200_MAX_FAST_CUTOFF) {
+    // a gate axis is the innermost one: staged kernel
+    const int rows = g.stride2 == 0 ? 1 : D;
+    cudaError_t e = cudaSuccess;
+#define B200_LAUNCH(N) \
+  case N:              \
+    e = launch_inner_d<N>(state, coef, g, tt, rows, nbatch, st); \
+    break;
+    switch (D) {
+      B200_LAUNCH(2) B200_LAUNCH(3) B200_LAUNCH(4) B200_LAUNCH(5) B200_LAUNCH(6) B200_LAUNCH(7) B200_LAUNCH(8)
+      B200_LAUNCH(9) B200_LAUNCH(10) B200_LAUNCH(11) B200_LAUNCH(12) B200_LAUNCH(13) B200_LAUNCH(14)
+      B200_LAUNCH(15) B200_LAUNCH(16)
+      default: break;
+    }
+#undef B200_LAUNCH
+    if (e != cudaSuccess) return fail((int)e, "apply: shared memory opt-in failed: %s", cudaGetErrorString(e));
+    return cuda_status("apply_inner");
+  }
   size_t smem = (size_t)g.coef_count * sizeof(cplx);
   unsigned n_groups = (g.n_slices + 31u) / 32u;
   // ~16 warp-tasks per CTA: two per warp, enough to amortise staging the gate table
