@@ -87,6 +87,34 @@ __device__ __forceinline__ void store_out(void* C, long long ic, cplx v, int fla
   else reinterpret_cast<cplx*>(C)[ic] = v;
 }
 
+// pure copy / product (no reduction): four output elements per thread, all loads issued before
+// the first store, so ~128 KB are in flight per SM (one element per thread left the kernel
+// latency-bound at a third of the HBM rate -- it is the pack/unpack of the multi-GPU exchange)
+constexpr int GC_UNROLL = 4;
+__global__ void __launch_bounds__(GR_THREADS)
+k_gather_copy(const b200_gather_desc d, const void* __restrict__ A, const cplx* __restrict__ B,
+              void* __restrict__ C, unsigned long long n_out, int flags) {
+  const unsigned long long tile = (unsigned long long)GR_THREADS * GC_UNROLL;
+  const unsigned long long o0 = (unsigned long long)blockIdx.x * tile + threadIdx.x;
+  OutOffsets off[GC_UNROLL];
+  cplx v[GC_UNROLL];
+#pragma unroll
+  for (int u = 0; u < GC_UNROLL; ++u) {
+    unsigned long long o = o0 + (unsigned long long)u * GR_THREADS;
+    if (o < n_out) off[u] = decode_out(d, o);
+  }
+#pragma unroll
+  for (int u = 0; u < GC_UNROLL; ++u) {
+    unsigned long long o = o0 + (unsigned long long)u * GR_THREADS;
+    if (o < n_out) v[u] = load_term(A, B, off[u].a, off[u].b, flags);
+  }
+#pragma unroll
+  for (int u = 0; u < GC_UNROLL; ++u) {
+    unsigned long long o = o0 + (unsigned long long)u * GR_THREADS;
+    if (o < n_out) store_out(C, off[u].c, v[u], flags);
+  }
+}
+
 // one thread per output element, sequential reduction (small n_red)
 __global__ void __launch_bounds__(GR_THREADS)
 k_gather_thread(const b200_gather_desc d, const void* __restrict__ A, const cplx* __restrict__ B,
@@ -243,7 +271,14 @@ int b200_gather_reduce(const b200_gather_desc* desc, const void* A_dev, const b2
     n_red *= (unsigned long long)desc->red_ext[j];
   }
   cudaStream_t st = (cudaStream_t)stream;
-  if (desc->n_red_axes == 0 || n_red <= 64 || n_out >= (1ull << 16)) {
+  if (desc->n_red_axes == 0) {
+    unsigned long long per = (unsigned long long)GR_THREADS * GC_UNROLL;
+    unsigned long long blocks = (n_out + per - 1) / per;
+    B200_CHECK_ARG(blocks < (1ull << 31), "gather_reduce: output too large for one launch");
+    k_gather_copy<<<(unsigned)blocks, GR_THREADS, 0, st>>>(*desc, A_dev, (const cplx*)B_dev, C_dev, n_out, flags);
+    return cuda_status("gather_copy");
+  }
+  if (n_red <= 64 || n_out >= (1ull << 16)) {
     unsigned long long blocks = (n_out + GR_THREADS - 1) / GR_THREADS;
     B200_CHECK_ARG(blocks < (1ull << 31), "gather_reduce: output too large for one launch");
     k_gather_thread<<<(unsigned)blocks, GR_THREADS, 0, st>>>(*desc, A_dev, (const cplx*)B_dev, C_dev, n_out,
