@@ -234,7 +234,7 @@ def b200_arm(args):
     be.circuit.profile = None
     by_tag = {}
     for tag, nbytes, a, b in prof:
-        if tag == "exchange":  # reported separately (NVLink, not HBM)
+        if tag.startswith("exchange"):  # reported separately (NVLink, not HBM)
             continue
         t = a.elapsed_time(b) * 1e-3
         d = by_tag.setdefault(tag, [0, 0.0, 0])
@@ -352,6 +352,11 @@ def b200_arm(args):
                     (sum(nb for nb, _ in ex) / sum(t for _, t in ex) / 1e9) if ex else None,
                 "exchanges_in_timed_region": int(exchanges),
             }
+            for part in ("pack", "all_to_all", "unpack"):
+                sel = [(nb, a.elapsed_time(b) * 1e-3) for tag, nb, a, b in prof if tag == "exchange/" + part]
+                if sel:
+                    line["exchange"][part] = {"ms": sum(t for _, t in sel) / len(sel) * 1e3,
+                                              "GBps": sum(nb for nb, _ in sel) / sum(t for _, t in sel) / 1e9}
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))

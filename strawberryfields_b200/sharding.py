@@ -213,8 +213,16 @@ class ShardedCircuit(DeviceCircuit):
             src.append(ls[pos])
         dstc = self._contig(exts)
         self._gather(self._buf, None, self._send, [(e, s, 0, c) for e, s, c in zip(exts, src, dstc)])
+        if prof is not None:
+            eva = torch.cuda.Event(enable_timing=True)
+            eva.record()
         # ---- all-to-all: block q of `send` goes to rank q ----
         dist.all_to_all_single(self._recv.view(torch.float64), self._send.view(torch.float64), group=self._pg)
+        if prof is not None:
+            evb = torch.cuda.Event(enable_timing=True)
+            evb.record()
+            prof.append(("exchange/pack", 32 * size, ev0, eva))
+            prof.append(("exchange/all_to_all", 16 * size * (self._world - 1) // self._world, eva, evb))
         # ---- unpack: recv[b_0..b_{g-1}][j_0..][.. m_k at T[k] ..] -> new local tensor ----
         rs = dict()  # name -> stride inside recv
         names = [("b", k) for k in range(g)] + [("j", k) for k in range(g)] + [("l", pos) for pos in range(g, n)]
@@ -233,6 +241,7 @@ class ShardedCircuit(DeviceCircuit):
         self._gather(self._recv, None, self._buf, oa)
         if prof is not None:
             ev1.record()
+            prof.append(("exchange/unpack", 32 * size, evb, ev1))
             prof.append(("exchange", 16 * size * (self._world - 1) // self._world, ev0, ev1))
         phys = list(self._phys)
         for k in range(g):
