@@ -171,7 +171,7 @@ def b200_arm(args):
     # the N GPUs (strong scaling), gates on sharded modes served by the all-to-all axis exchange.
     sharded = world > 1
     D = args.cutoff
-    shard_kw = {"shard": True} if sharded else {}
+    shard_kw = {"shard": True, "exchange": args.exchange} if sharded else {}
     if args.workload == "c3":      # BASELINE config 3: 4-mode MIXED state, S/BS layers + LossChannel(0.9)
         n_modes = args.modes or 4
         calls = W.config3_circuit(n_modes, seed=42)
@@ -285,10 +285,12 @@ def b200_arm(args):
             o[m] = k
             outcomes.append(o)
 
+    be2 = B200FockBackend()
+    be2.begin_circuit(n_modes, cutoff_dim=D, fuse=fuse, **shard_kw)
+
     def e2e_step():
         dev_params = pinned.to("cuda", non_blocking=True)  # H2D of the step's inputs
-        be2 = B200FockBackend()
-        be2.begin_circuit(n_modes, cutoff_dim=D, fuse=fuse, **shard_kw)
+        be2.reset(pure=args.workload != "c3")  # what LocalEngine.reset() does between runs (engine.py:413-417)
         for i, c in enumerate(calls):
             modes = [x for x in c[1:] if isinstance(x, (int, np.integer))]
             getattr(be2, c[0])(*([DeviceParams(dev_params[i])] + ([None] if c[0] in two_param else []) + modes))
@@ -352,7 +354,9 @@ def b200_arm(args):
                     (sum(nb for nb, _ in ex) / sum(t for _, t in ex) / 1e9) if ex else None,
                 "exchanges_in_timed_region": int(exchanges),
             }
-            for part in ("pack", "all_to_all", "unpack"):
+            line["exchange"]["mode"] = ("peer-memory pull kernel (NVLink P2P loads, no staging)"
+                                        if getattr(be.circuit, "_p2p", False) else "pack + NCCL all_to_all + unpack")
+            for part in ("p2p_pull", "pack", "all_to_all", "unpack"):
                 sel = [(nb, a.elapsed_time(b) * 1e-3) for tag, nb, a, b in prof if tag == "exchange/" + part]
                 if sel:
                     line["exchange"][part] = {"ms": sum(t for _, t in sel) / len(sel) * 1e3,
@@ -376,6 +380,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"],
                     help="c2 (default; c5 when sharded over N > 1 GPUs), c3 = mixed state + loss, c4 = batched QNN layer")
     ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="multi-GPU axis exchange: peer-memory pull kernel or pack + NCCL all-to-all + unpack")
     ap.add_argument("--fuse", default="fold", choices=["tile", "fold", "off"],
                     help="gate queue: tile passes (default), diagonal folding only, or one pass per gate")
     args = ap.parse_args()

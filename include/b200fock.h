@@ -69,6 +69,9 @@ int64_t b200_packed_size(int D);
 /* kernel launches issued by this process through the library since load / last reset */
 int64_t b200_launch_count(void);
 void b200_reset_launch_count(void);
+/* let kernels launched on the current device dereference pointers that live on `peer_device`
+ * (NVLink peer access; the multi-GPU exchange reads other ranks' shards directly) */
+int b200_enable_peer_access(int peer_device);
 
 /* ---- gate tables, generated on the device (reference: thewalrus.fock_gradients
  *      called from fockbackend/ops.py:233,252,266,326,340) -----

@@ -153,7 +153,8 @@ class B200FockBackend(_Base):
             if not pure or batch_size is not None:
                 raise NotImplementedError("sharded b200fock circuits hold unbatched pure states only")
             group = None if shard is True else shard
-            self.circuit = ShardedCircuit(num_subsystems, cutoff_dim, group=group, **self._options)
+            self.circuit = ShardedCircuit(num_subsystems, cutoff_dim, group=group,
+                                          exchange=kwargs.get("exchange", "auto"), **self._options)
         else:
             self.circuit = DeviceCircuit(num_subsystems, cutoff_dim, pure, batch_size=batch_size, **self._options)
         self._modemap = ModeMap(num_subsystems)

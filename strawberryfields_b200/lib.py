@@ -71,6 +71,7 @@ SIGNATURES = {
     "b200_packed_size": [_I],
     "b200_launch_count": [],
     "b200_reset_launch_count": [],
+    "b200_enable_peer_access": [_I],
     "b200_gen_gate1": [_I, _I, _I, _D, _D, _P, _P, _P],
     "b200_gen_diag": [_I, _I, _I, _D, _P, _P, _P],
     "b200_gen_gate2": [_I, _I, _I, _D, _D, _P, _P, _P],

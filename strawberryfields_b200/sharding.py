@@ -54,20 +54,32 @@ class ShardedCircuit(DeviceCircuit):
         self._pg = group
         self._rank = dist.get_rank(group)
         self._world = dist.get_world_size(group)
-        self._ps = factor_world(self._world, trunc)
-        self._g = len(self._ps)
+        self._set_factors(trunc)
         if self._g > num - 1:
             raise ValueError("%d modes are too few to shard over %d ranks at cutoff %d" % (num, self._world, trunc))
-        digits, r = [], self._rank
-        for p in reversed(self._ps):
-            digits.append(r % p)
-            r //= p
-        self._digits = list(reversed(digits))  # b_0 .. b_{g-1}, b_0 most significant
         self.exchanges = 0
         self.exchange_bytes = 0
+        # "p2p": one gather kernel per source rank reads the peers' shards straight over NVLink (no
+        # pack / unpack, no staging buffers); "nccl": pack -> all_to_all_single -> unpack; "auto": p2p
+        # when every rank can map every peer's buffers, else nccl
+        self._xmode = opts.pop("exchange", "auto")
+        self._p2p = False
+        self._bufs = None
         opts.pop("batch_size", None)
         opts["fuse"] = "fold"
         super().__init__(num, trunc, pure=True, **opts)
+
+    def _set_factors(self, D):
+        self._ps = factor_world(self._world, D)
+        self._g = len(self._ps)
+        self._digits = self._digits_of(self._rank)  # b_0 .. b_{g-1}, b_0 most significant
+
+    def _digits_of(self, rank):
+        digits, r = [], rank
+        for p in reversed(self._ps):
+            digits.append(r % p)
+            r //= p
+        return list(reversed(digits))
 
     # ------------------------------------------------------------------ geometry
     def _ext(self, pos):
@@ -102,13 +114,20 @@ class ShardedCircuit(DeviceCircuit):
             self._num_modes = num_subsystems
         if cutoff_dim is not None:
             if cutoff_dim != getattr(self, "_trunc", cutoff_dim):
-                self._ps = factor_world(self._world, cutoff_dim)
-                self._g = len(self._ps)
+                self._set_factors(cutoff_dim)
             self._trunc = cutoff_dim
         self._pure = True
         self._scratch = self._send = self._recv = None
         self._shared = False
-        self._buf = self._new(self._size())
+        size = self._size()
+        if self._bufs is None or self._bufs[0].numel() != size:
+            # two state buffers (ping-pong target of the exchange), mapped into every peer when possible
+            self._bufs = None
+            self._buf = None
+            self._bufs = [self._new(size)]
+            self._p2p = self._setup_p2p(size)
+        self._cur = 0
+        self._buf = self._bufs[0]
         L.call("b200_fill_zero", _ptr(self._buf), self._buf.numel(), self._stream())
         if self._rank == 0:
             L.call("b200_set_element", _ptr(self._buf), 0, 1.0, 0.0, self._stream())
@@ -176,6 +195,90 @@ class ShardedCircuit(DeviceCircuit):
             local.sort(reverse=True)
             self._exchange(sorted(pos for _, _, pos in local[:g]))
 
+    # ------------------------------------------------------------------ peer mapping (NVLink P2P)
+    def _setup_p2p(self, size):
+        """Map both state buffers of every rank into this process (CUDA IPC through torch's storage
+        sharing) and enable peer access, so that a kernel here can read a peer's shard directly.
+        Collective; returns True only if it worked on every rank."""
+        if self.device.type != "cuda" or self._xmode == "nccl" or self._world == 1:
+            return False
+        ok = True
+        peers = None
+        try:
+            self._bufs.append(self._new(size))
+            shared = []
+            for b in self._bufs:
+                shared.append((b.untyped_storage()._share_cuda_(), b.storage_offset()))
+            everyone = [None] * self._world
+            dist.all_gather_object(everyone, (self.device.index, shared), group=self._pg)
+            peers = [[None] * self._world for _ in range(2)]
+            for r, (dev, sh) in enumerate(everyone):
+                for i in range(2):
+                    if r == self._rank:
+                        peers[i][r] = self._bufs[i]
+                        continue
+                    L.call("b200_enable_peer_access", int(dev))
+                    handle, offset = sh[i]
+                    st = torch.UntypedStorage._new_shared_cuda(*handle)
+                    typed = torch.storage.TypedStorage(wrap_storage=st, dtype=torch.complex128, _internal=True)
+                    peers[i][r] = torch._utils._rebuild_tensor(typed, offset, (size,), (1,))
+        except Exception as exc:  # no IPC / no peer path on this box: fall back to the NCCL exchange
+            ok = False
+            self._p2p_error = repr(exc)
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self._pg)
+        ok = bool(flag.item())
+        if ok:
+            self._peers = peers
+        else:
+            if self._xmode == "p2p":
+                raise L.B200Error("peer-memory exchange requested but not available: %s"
+                                  % getattr(self, "_p2p_error", "a peer failed"))
+            self._bufs = self._bufs[:1]
+            self._peers = None
+        return ok
+
+    def _exchange_p2p(self, T):
+        """Exchange without staging: for every source rank, ONE strided-gather launch reads that
+        rank's block of the old layout straight out of its HBM over NVLink and writes it where it
+        belongs in this rank's new shard (the other ping-pong buffer)."""
+        g, n, D = self._g, self._num_modes, self._trunc
+        size = self._size()
+        ls = [self._local_stride(p) for p in range(n)]
+        sub = [D // p for p in self._ps]
+        prof = self.__dict__.get("profile")
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self._pg)  # every rank's current shard is final and may be read
+        if prof is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+        dst = self._bufs[1 - self._cur]
+        oa = []
+        for pos in range(n):
+            if pos < g:                       # new sharded remainder m_k <- source axis T[k]
+                oa.append((sub[pos], ls[T[pos]], 0, ls[pos]))
+            elif pos in T:                    # new local axis T[k] <- source's remainder j_k on axis k
+                k = T.index(pos)
+                oa.append((sub[k], ls[k], 0, ls[pos]))
+            else:
+                oa.append((D, ls[pos], 0, ls[pos]))
+        base_a = sum(self._digits[k] * sub[k] * ls[T[k]] for k in range(g))  # my digit selects what I pull
+        for step in range(self._world):
+            s = (self._rank + step) % self._world   # start with the local block, then walk the ring
+            sd = self._digits_of(s)
+            base_c = sum(sd[k] * sub[k] * ls[T[k]] for k in range(g))  # the sender's digit lands on axis T[k]
+            self._gather(self._peers[self._cur][s], None, dst, oa, base=(base_a, 0, base_c))
+        if prof is not None:
+            ev1.record()
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self._pg)  # nobody still reads the old shards
+        if prof is not None:
+            nbytes = 16 * size * (self._world - 1) // self._world
+            prof.append(("exchange/p2p_pull", nbytes, ev0, ev1))
+            prof.append(("exchange", nbytes, ev0, ev1))
+        self._cur ^= 1
+        self._buf = dst
+
     # ------------------------------------------------------------------ the exchange
     def _contig(self, exts):
         st, acc = [], 1
@@ -185,9 +288,27 @@ class ShardedCircuit(DeviceCircuit):
         return list(reversed(st))
 
     def _exchange(self, T):
-        """Swap sharded axis k with local axis T[k] for every k (one all-to-all)."""
-        g, n, D = self._g, self._num_modes, self._trunc
+        """Swap sharded axis k with local axis T[k] for every k."""
+        g, n = self._g, self._num_modes
         assert len(T) == g and all(t >= g for t in T)
+        if self._p2p:
+            self._exchange_p2p(T)
+        else:
+            self._exchange_nccl(T)
+        phys = list(self._phys)
+        for k in range(g):
+            phys[k], phys[T[k]] = phys[T[k]], phys[k]
+        self._phys = phys
+        pos = [0] * n
+        for p, v in enumerate(phys):
+            pos[v] = p
+        self._pos = pos
+        self.exchanges += 1
+        self.exchange_bytes += 16 * self._size() * (self._world - 1) // self._world
+
+    def _exchange_nccl(self, T):
+        """pack (strided gather) -> all_to_all_single -> unpack (strided gather)."""
+        g, n, D = self._g, self._num_modes, self._trunc
         size = self._size()
         if self._send is None:
             self._send, self._recv = self._new(size), self._new(size)
@@ -243,16 +364,6 @@ class ShardedCircuit(DeviceCircuit):
             ev1.record()
             prof.append(("exchange/unpack", 32 * size, evb, ev1))
             prof.append(("exchange", 16 * size * (self._world - 1) // self._world, ev0, ev1))
-        phys = list(self._phys)
-        for k in range(g):
-            phys[k], phys[T[k]] = phys[T[k]], phys[k]
-        self._phys = phys
-        pos = [0] * n
-        for p, v in enumerate(phys):
-            pos[v] = p
-        self._pos = pos
-        self.exchanges += 1
-        self.exchange_bytes += 16 * size * (self._world - 1) // self._world
 
     # ------------------------------------------------------------------ observation
     def _norm_device(self):
@@ -312,8 +423,15 @@ class ShardedCircuit(DeviceCircuit):
         snap._pending, snap._opq, snap._untouched = {}, [], set()
         snap._scratch = snap._send = snap._recv = snap._part = None
         snap._norm_part = torch.zeros(4096, dtype=torch.float64, device=self.device)
-        snap._shared = True
-        self._shared = True
+        if self._p2p:
+            # the live buffers are mapped into the peers and reused in place: the state object gets
+            # its own copy instead of a copy-on-write share
+            snap._buf = self._buf.clone()
+            snap._bufs, snap._peers, snap._p2p = None, None, False
+            snap._shared = False
+        else:
+            snap._shared = True
+            self._shared = True
         return snap
 
     # ------------------------------------------------------------------ not sharded yet

@@ -37,7 +37,8 @@ def main():
     extra = [("mzgate", 0.4, 1.1, 0, n - 1), ("two_mode_squeeze", 0.2, 0.3, n - 1, 1), ("kerr_interaction", 0.1, 0),
              ("beamsplitter", 0.7, 0.2, 1, 0)]
     be = B200FockBackend()
-    be.begin_circuit(n, cutoff_dim=D, shard=True)
+    exchange = sys.argv[4] if len(sys.argv) > 4 else "auto"
+    be.begin_circuit(n, cutoff_dim=D, shard=True, exchange=exchange)
     W.run_calls(be, calls + extra)
     st = be.state()
     ket = st.ket()
@@ -52,7 +53,7 @@ def main():
     ok = bool(err < 1e-12 and tr_err < 1e-12 and fp_err < 1e-12)
     print(json.dumps({"rank": dist.get_rank(), "world": dist.get_world_size(), "err": err,
                       "trace_err": float(tr_err), "fock_prob_err": float(fp_err),
-                      "exchanges": int(be.circuit.exchanges), "ok": ok}))
+                      "exchanges": int(be.circuit.exchanges), "p2p": bool(be.circuit._p2p), "ok": ok}))
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

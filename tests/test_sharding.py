@@ -21,10 +21,10 @@ def _free_port():
     return port
 
 
-def _run(mode, world, n, D):
+def _run(mode, world, n, D, exchange="auto"):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
-           os.path.join(ROOT, "tests", "dist_worker.py"), mode, str(n), str(D)]
+           os.path.join(ROOT, "tests", "dist_worker.py"), mode, str(n), str(D), exchange]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     import re
 
@@ -53,10 +53,13 @@ def test_sharded_circuit_matches_oracle_gloo(world, n, D):
 
 
 @pytest.mark.gpu
-def test_sharded_circuit_matches_oracle_nccl():
+@pytest.mark.parametrize("exchange", ["nccl", "p2p"])
+def test_sharded_circuit_matches_oracle_on_gpus(exchange):
+    """NCCL all-to-all exchange and the peer-memory pull kernel give the oracle's ket."""
     import torch
 
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
     world = 2 if torch.cuda.device_count() < 4 else 4
-    _run("gpu", world, 5, 6)
+    lines = _run("gpu", world, 5, 6, exchange)
+    assert all(l["p2p"] == (exchange == "p2p") for l in lines)
