@@ -219,6 +219,9 @@ class ShardedCircuit(DeviceCircuit):
                         continue
                     L.call("b200_enable_peer_access", int(dev))
                     handle, offset = sh[i]
+                    # open the IPC handle in THIS device's context (cudaIpcMemLazyEnablePeerAccess maps
+                    # the exporter's memory for peer loads from here), not in the exporter's
+                    handle = (self.device.index,) + tuple(handle[1:])
                     st = torch.UntypedStorage._new_shared_cuda(*handle)
                     typed = torch.storage.TypedStorage(wrap_storage=st, dtype=torch.complex128, _internal=True)
                     peers[i][r] = torch._utils._rebuild_tensor(typed, offset, (size,), (1,))
