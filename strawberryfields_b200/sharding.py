@@ -190,11 +190,10 @@ class ShardedCircuit(DeviceCircuit):
                     next_use.setdefault(a, rank_)
             # ties: keep the two innermost axes for the residents -- the modes coming in are used at
             # once, and the streaming kernels are slowest on the last two axes
-            # Never evict the two innermost axes if it can be avoided: swapping them would cut the
-            # exchange into 16*D/p-byte (80 B) runs -- measured 110 GB/s instead of 590 GB/s over NVLink --
-            # and the modes coming in are used at once, where the streaming kernels are slowest.
+            # Never evict the innermost axis if it can be avoided: swapping it would cut the exchange
+            # into 16*D/p-byte (80 B) runs -- measured 110 GB/s instead of 590 GB/s over NVLink.
             n = self._num_modes
-            cand = list(range(g, n - 2)) if n - 2 - g >= g else list(range(g, n))
+            cand = list(range(g, n - 1)) if n - 1 - g >= g else list(range(g, n))
             local = [(next_use.get(self._phys[pos], 1 << 30), pos) for pos in cand]
             local.sort(reverse=True)
             self._exchange(sorted(pos for _, pos in local[:g]))
