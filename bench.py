@@ -49,6 +49,21 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel, elements_per_launch):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture
+    (profiles/r01_ncu_traffic.json, taken on config 2: 1e8 amplitudes per launch); None for any
+    other launch size -- never extrapolated."""
+    path = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    if not os.path.exists(path) or elements_per_launch != 10 ** 8:
+        return None
+    with open(path) as f:
+        table = json.load(f)["bytes_per_launch"]
+    for name, val in table.items():
+        if kernel in name:
+            return val
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
@@ -241,7 +256,7 @@ def b200_arm(args):
         d[0] += nbytes
         d[1] += t
         d[2] += 1
-    kernels = {"k_tile_pass": "tile", "k_apply_blocks": "gate", "k_apply_diag": "diag"}
+    kernels = {"k_tile_pass": "tile", "k_apply_blocks": "gate", "k_apply_inner": "inner", "k_apply_diag": "diag"}
     groups = {}
     for kname, prefix in kernels.items():
         sel = [v for tag, v in by_tag.items() if tag.startswith(prefix)]
@@ -254,7 +269,7 @@ def b200_arm(args):
     roofline = {
         "kernel": dom_kernel, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
         "share_of_step_time": dom_time / max(sum(g[1] for g in groups.values()), 1e-12),
-        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "frac": achieved / peak, "traffic": ncu_traffic(dom_kernel, local_elements), "peak_source": peak_src,
         "launches_per_step": dom_n, "avg_launch_ms": dom_time / max(dom_n, 1) * 1e3,
         "algorithmic_bytes_per_launch": 32 * local_elements,
         "frac_of_nominal_8TBs": achieved / 8000.0,

@@ -328,7 +328,10 @@ class DeviceCircuit:
         D, B = self._trunc, self._B
         nb = G.shape[0]
         naxes = self._axes()
-        self._pass("gate2/rule%d/axes%d,%d" % (rule, naxes - 1 - self._pos[ax1], naxes - 1 - self._pos[ax2]),
+        # the C side routes pair gates with an axis of stride 1 to the staged kernel (k_apply_inner)
+        staged = min(self._stride(ax1), self._stride(ax2)) == 1 and 2 <= D <= L.MAX_FAST_CUTOFF
+        self._pass("%s/rule%d/axes%d,%d" % ("inner2" if staged else "gate2", rule, naxes - 1 - self._pos[ax1],
+                                            naxes - 1 - self._pos[ax2]),
                    "b200_apply_gate2",
                    _ptr(self._buf), self._size(), D, self._stride(ax1), self._stride(ax2),
                rule, _ptr(G), int(conj), B, self._size(), G.shape[1] if nb > 1 else 0, self._stream())
