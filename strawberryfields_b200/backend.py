@@ -206,6 +206,15 @@ class B200FockBackend(_Base):
     def prepare_dm_state(self, state, modes):
         self.circuit.prepare_multimode(state, self._remap_modes(modes))
 
+    def prepare_gkp(self, state, epsilon, ampl_cutoff, representation="real", shape="square", mode=None):
+        """Finite-energy GKP qubit state ``[theta, phi]`` (backend.py:297-329)."""
+        if representation == "complex":
+            raise NotImplementedError("The complex description of GKP is not implemented")
+        if shape != "square":
+            raise NotImplementedError("Only square GKP are implemented for now")
+        theta, phi = state[0], state[1]
+        self.circuit.prepare_gkp(theta, phi, epsilon, ampl_cutoff, self._remap_modes(mode))
+
     # -- gates (backend.py:166-182, 279-288) ------------------------------------------------
     def rotation(self, phi, mode):
         self.circuit.phase_shift(phi, self._remap_modes(mode))

@@ -1091,6 +1091,11 @@ class DeviceCircuit:
         return np.array([[sample]])
 
 
+    def prepare_gkp(self, theta, phi, epsilon, ampl_cutoff, mode):
+        """Finite-energy square-lattice GKP qubit state (circuit.py:803-812): a host-built ket."""
+        self._prepare_ket(_square_gkp_state(theta, phi, epsilon, ampl_cutoff, self._trunc), mode)
+
+
 # ---------------------------------------------------------------------- host-built single-mode kets
 def _coherent(r, phi, D):
     alpha = r * np.exp(1j * phi)
@@ -1104,6 +1109,24 @@ def _squeezed(r, theta, D):
         m = n // 2
         v[n] = (np.sqrt(factorial(2 * m)) / (2 ** m * factorial(m))) * (-np.exp(1j * theta) * np.tanh(r)) ** m
     return np.sqrt(1 / np.cosh(r)) * v
+
+
+def _square_gkp_state(theta, phi, epsilon, ampl_cutoff, D):
+    """cos(theta/2)|0>_gkp + e^{-i phi} sin(theta/2)|1>_gkp with Fock-damped (epsilon) basis states:
+    each basis state is a Gaussian-weighted comb of displaced squeezed states
+    (fockbackend/ops.py:518-596)."""
+    def basis(k):
+        z_max = int(np.ceil(np.sqrt(-0.25 / np.pi * np.log(ampl_cutoff) / np.tanh(epsilon))))
+        r = -0.5 * np.log(np.tanh(epsilon))
+        ket = np.zeros(D, dtype=C128)
+        for t in range(-z_max, z_max + 1):
+            weight = np.exp(-0.5 * np.pi * np.tanh(epsilon) * (k + 2 * t) ** 2)
+            alpha = np.sqrt(0.5 * np.pi) * (2 * t + k) / np.cosh(epsilon)
+            ket = ket + weight * _displaced_squeezed(alpha, 0, r, 0, D)
+        return ket
+
+    ket = np.cos(theta / 2) * basis(0) + np.sin(theta / 2) * np.exp(-1j * phi) * basis(1)
+    return ket / np.linalg.norm(ket)
 
 
 def _displaced_squeezed(r_d, phi_d, r_s, phi_s, D):

@@ -25,3 +25,17 @@ def test_engine_drop_in():
     assert out["dm_err"] < 1e-12
     assert out["mean_photon_err"] < 1e-10
     assert out["wigner_shape"] == [5, 5]
+
+
+@pytest.mark.reference
+def test_reference_suite_subset_runs_on_b200fock():
+    """Three files of the reference's own backend test-suite (beamsplitter on every mode pair, loss
+    channel, Fock measurement) with FockBackend swapped for B200FockBackend (tests/b200_ref_plugin.py).
+    The full run is recorded in profiles/r01_reference_suite.md."""
+    files = ["test_beamsplitter_operation.py", "test_loss_channel.py", "test_fock_measurement.py"]
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([ROOT, os.path.join(ROOT, "tests")]))
+    res = subprocess.run([sys.executable, "-m", "pytest", "-p", "b200_ref_plugin", "-p", "no:cacheprovider", "-m", "fock",
+                          "-q"] + [os.path.join("/root/reference/tests/backend", f) for f in files],
+                         capture_output=True, text=True, timeout=900, cwd="/tmp", env=env)
+    tail = res.stdout.strip().splitlines()[-1]
+    assert res.returncode == 0 and " passed" in tail and "failed" not in tail, res.stdout[-2000:]
