@@ -166,6 +166,66 @@ def reference_arm(args):
     print(json.dumps(line))
 
 
+def c1_arm(args):
+    """BASELINE config 1 (examples/boson_sampling.py, 4 modes, cutoff 7): a launch-latency-bound
+    circuit.  One step = begin_circuit + 4 preparations + 12 gates + all_fock_probs() on the host.
+    The reference turns the state into a 7^8-element density tensor at the first Fock preparation
+     and needs ~15 s; b200fock keeps the 7^4-amplitude ket."""
+    import torch
+
+    from strawberryfields_b200 import B200FockBackend, lib
+    from strawberryfields_b200 import workloads as W
+
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    handle = lib.load(build_if_missing=False)
+    calls = W.config1_circuit()
+    n_gates = len([c for c in calls if not c[0].startswith("prepare")])
+    be = B200FockBackend()
+
+    def step():
+        be.begin_circuit(4, cutoff_dim=7)
+        W.run_calls(be, calls)
+        return be.state().all_fock_probs()
+
+    for _ in range(max(args.warmup, 3)):
+        probs = step()
+    torch.cuda.synchronize()
+    handle.b200_reset_launch_count()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        probs = step()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / args.steps
+    launches = int(handle.b200_launch_count())
+    ok = abs(probs[1, 1, 0, 1] - 0.174689160486) < 1e-10 and abs(probs[2, 0, 0, 1] - 0.106441927246) < 1e-10
+    line = {
+        "metric": METRIC, "value": n_gates * 7 ** 4 / dt, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "complex128", "data": "synthetic",
+        "config": {"workload": "BASELINE config 1: examples/boson_sampling.py, 4 modes, cutoff 7, pure ket of 2401 "
+                               "amplitudes (the reference holds a 7^8 density tensor), 12 gates + all_fock_probs()",
+                   "bound": "kernel-launch / host latency, not HBM"},
+        "e2e": {"value": n_gates * 7 ** 4 / dt, "unit": UNIT, "h2d_bytes_per_step": 4 * 7 * 16,
+                "d2h_bytes_per_step": 8 * 7 ** 4},
+        "gpu_launches": launches, "circuit_ms": dt * 1e3,
+        "golden_probabilities_ok": bool(ok),
+    }
+    if not args.no_cpu_baseline:
+        from oracle.fock_oracle import OracleBackend
+
+        ob = OracleBackend(style="reference")
+        t0 = time.perf_counter()
+        ob.begin_circuit(4, cutoff_dim=7)
+        W.run_calls(ob, calls)
+        ob.state().all_fock_probs()
+        tc = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": n_gates * 7 ** 8 / tc, "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": "the whole config-1 circuit on the reference's 7^8-element mixed "
+                                          "representation, incl. numba JIT: %.1f s" % tc,
+                                "circuit_ms": tc * 1e3}
+    print(json.dumps(line))
+
+
 # ------------------------------------------------------------------------------ b200 arm
 def b200_arm(args):
     import torch
@@ -392,7 +452,7 @@ def main():
     ap.add_argument("--modes", type=int, default=0, help="default: 8 on one GPU, 9 sharded")
     ap.add_argument("--cutoff", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"],
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4"],
                     help="c2 (default; c5 when sharded over N > 1 GPUs), c3 = mixed state + loss, c4 = batched QNN layer")
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
@@ -402,6 +462,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
+    elif args.workload == "c1":
+        c1_arm(args)
     else:
         b200_arm(args)
 

@@ -58,6 +58,20 @@ def interferometer_unitary(N, calls):
     return U
 
 
+def config1_circuit():
+    """BASELINE config 1: ``examples/boson_sampling.py:5-41`` (fixed literals): Fock inputs
+    |1,1,0,1>, four Rgates, eight BSgates on 4 modes; the result is ``all_fock_probs()``."""
+    calls = [("prepare_fock_state", 1, 0), ("prepare_fock_state", 1, 1), ("prepare_vacuum_state", 2),
+             ("prepare_fock_state", 1, 3)]
+    for m, t in enumerate((0.5719, -1.9782, 2.0603, 0.0644)):
+        calls.append(("rotation", t, m))
+    for t, p, a, b in ((0.7804, 0.8578, 0, 1), (0.06406, 0.5165, 2, 3), (0.473, 0.1176, 1, 2),
+                       (0.563, 0.1517, 0, 1), (0.1323, 0.9946, 2, 3), (0.311, 0.3231, 1, 2),
+                       (0.4348, 0.0798, 0, 1), (0.4368, 0.6157, 2, 3)):
+        calls.append(("beamsplitter", t, p, a, b))
+    return calls
+
+
 def config2_circuit(N=8, seed=42):
     """BASELINE config 2 / 5: Sgate + Dgate on every mode, then a random N-mode
     interferometer.  N=8: 8 S + 8 D + 36 R + 28 BS = 80 gates."""
