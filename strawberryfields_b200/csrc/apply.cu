@@ -357,9 +357,15 @@ static cudaError_t launch_inner_d(cplx* state, const cplx* coef, const Geometry&
                                   int nbatch, cudaStream_t st) {
   const int spc = rows == 1 ? inner_threads(D) : 32;  // slices per CTA: one per thread / one lane group
   const int SL = (rows * D) | 1;
-  // persistent 4-stage pipeline when the launch is unbatched and four stages fit in shared memory
+  // Persistent 4-stage pipeline (unbatched launches, four stages must fit in shared memory).  Measured
+  // on B200 at D = 10: 3.7-3.9 TB/s against 3.97 TB/s for the one-shot kernel below -- the staged compute,
+  // not the bytes in flight, is the limit -- so it is off unless B200_INNER_PIPE=1 (kept for round 2).
+  static const bool pipe_on = [] {
+    const char* v = getenv("B200_INNER_PIPE");
+    return v && v[0] == '1';
+  }();
   size_t smem_pipe = ((size_t)g.coef_count + (size_t)INNER_STAGES * spc * SL) * sizeof(cplx);
-  if (nbatch == 1 && smem_pipe <= 227 * 1024) {
+  if (pipe_on && nbatch == 1 && smem_pipe <= 227 * 1024) {
     static int sms = 0;
     if (sms == 0) {
       int dev = 0;
