@@ -988,6 +988,13 @@ class DeviceCircuit:
         L.call("b200_scale", _ptr(self._buf), self._buf.numel(), 1.0, 0.0, _ptr(nrm), 1 if self._pure else 0,
                self._stream())
 
+    @staticmethod
+    def _sample_index(dist):
+        """One categorical draw from numpy's global stream, exactly as circuit.py:682-686 does it."""
+        if sum(dist) != 1:
+            return np.random.choice(list(range(len(dist))), p=dist / sum(dist))
+        return np.random.choice(list(range(len(dist))), p=dist)
+
     def measure_fock(self, modes, select=None):
         if self._batched:
             raise NotImplementedError("measure_fock on a batched b200fock circuit is not supported yet")
@@ -1020,11 +1027,8 @@ class DeviceCircuit:
             dist = self.marginal_probs_device(keep)[0].cpu().numpy()
             # steps 3-6 of SURVEY Appendix B, with numpy itself so the draw is bit-identical
             dist = dist * ~np.isclose(dist, 0.0)
-            if sum(dist) != 1:
-                i = np.random.choice(list(range(len(dist))), p=dist / sum(dist))
-            else:
-                i = np.random.choice(list(range(len(dist))), p=dist)
-            digits = [i // D ** (len(measure) - 1 - m) % D for m in range(len(measure))]
+            i = self._sample_index(dist)
+            digits =[i // D ** (len(measure) - 1 - m) % D for m in range(len(measure))]
             permutation = np.argsort(measure)
             outcome = [0] * len(measure)
             for j in range(len(measure)):

@@ -440,9 +440,85 @@ class ShardedCircuit(DeviceCircuit):
             self._shared = True
         return snap
 
+    # ------------------------------------------------------------------ reductions / measurement
+    def marginal_probs_device(self, keep):
+        """Photon-number distribution of the (sorted) modes ``keep``, float64 [1, D^k], the same on
+        every rank: each rank reduces its shard into its own block of the table, then one all-reduce of
+        D^k doubles."""
+        self._flush()
+        n, D, g = self._num_modes, self._trunc, self._g
+        k = len(keep)
+        out = torch.zeros(D ** k, dtype=torch.float64, device=self.device)
+        oa, base_c = [], 0
+        for j, m in enumerate(keep):
+            pos, w = self._pos[m], D ** (k - 1 - j)
+            st = self._local_stride(pos)
+            if pos < g:
+                sub = D // self._ps[pos]
+                oa.append((sub, st, st, w))
+                base_c += self._digits[pos] * sub * w
+            else:
+                oa.append((D, st, st, w))
+        kept_pos = {self._pos[m] for m in keep}
+        red = [(self._ext(p), self._local_stride(p), self._local_stride(p)) for p in range(n) if p not in kept_pos]
+        self._gather(self._buf, self._buf, out, oa, red, flags=L.FLAG_CONJ_B | L.FLAG_REAL_OUT, base=(0, 0, base_c))
+        dist.all_reduce(out, group=self._pg)
+        return out.view(1, -1)
+
+    def fock_probs_device(self):
+        """all_fock_probs on every rank (small states only: D^n doubles per rank)."""
+        return self.marginal_probs_device(list(range(self._num_modes)))
+
+    def _make_local(self, modes):
+        """Bring every mode of ``modes`` onto a whole (unsharded) axis."""
+        g, n = self._g, self._num_modes
+        if all(self._pos[m] >= g for m in modes):
+            return
+        cand = [p for p in range(g, n) if self._phys[p] not in modes]
+        if len(cand) < g:
+            raise NotImplementedError("too many measured modes for a %d-rank sharded state" % self._world)
+        cand.sort(key=lambda p: (p == n - 1, p))  # keep the innermost axis resident if possible
+        self._exchange(sorted(cand[:g]))
+
+    def _sample_index(self, dist_):
+        """Every rank holds the same distribution and draws from its own numpy stream (so a seeded
+        program advances the stream on every rank as the reference does); rank 0's draw is
+        authoritative."""
+        i = DeviceCircuit._sample_index(dist_)
+        t = torch.tensor([int(i)], dtype=torch.int64, device=self.device)
+        dist.broadcast(t, src=dist.get_global_rank(self._pg, 0) if self._pg is not None else 0, group=self._pg)
+        return int(t.item())
+
+    def _project_reset(self, modes, values):
+        """|0..0><x| on whole-axis modes: rank-local, out of place (into the other ping-pong buffer
+        when the buffers are mapped into the peers)."""
+        n = self._num_modes
+        assert all(self._pos[m] >= self._g for m in modes)
+        if self._p2p:
+            out = self._bufs[1 - self._cur]
+        else:
+            out = self._get_scratch(self._buf.numel())
+        L.call("b200_fill_zero", _ptr(out), out.numel(), self._stream())
+        base_a = sum(int(v) * self._stride(m) for m, v in zip(modes, values))
+        mpos = {self._pos[m] for m in modes}
+        oa = [(self._ext(p), self._local_stride(p), 0, self._local_stride(p)) for p in range(n) if p not in mpos]
+        self._gather(self._buf, None, out, oa, base=(base_a, 0, 0))
+        if self._p2p:
+            self._cur ^= 1
+            self._buf = out
+        elif self._shared:
+            self._buf, self._scratch, self._shared = out, None, False
+        else:
+            self._buf, self._scratch = out, self._buf
+            self._bufs = [self._buf]
+
+    def measure_fock(self, modes, select=None):
+        self._flush()
+        self._make_local(list(modes))
+        return DeviceCircuit.measure_fock(self, modes, select)
+
     # ------------------------------------------------------------------ not sharded yet
     def _unsupported(self, *a, **k):
         raise NotImplementedError("this operation is not available on a sharded b200fock circuit yet")
 
-    prepare_multimode = alloc = dealloc = measure_fock = measure_homodyne = _unsupported
-    marginal_probs_device = reduced_dm_device = fock_probs_device = _unsupported
+    prepare_multimode = alloc = dealloc = measure_homodyne = reduced_dm_device = _unsupported

@@ -50,7 +50,16 @@ def main():
     tr_err = abs(st.trace() - np.vdot(want, want).real)
     idx = [1] + [0] * (n - 2) + [2 % D]
     fp_err = abs(st.fock_prob(idx) - np.abs(want[tuple(idx)]) ** 2)
-    ok = bool(err < 1e-12 and tr_err < 1e-12 and fp_err < 1e-12)
+    # reductions: all_fock_probs (local reduce + all-reduce), then a seeded MeasureFock on a sharded and
+    # a local mode: same outcome and same post-measurement ket as the oracle
+    probs_err = float(np.abs(st.all_fock_probs() - np.abs(want) ** 2).max())
+    np.random.seed(5)
+    got_out = be.measure_fock([0, n - 1])
+    np.random.seed(5)
+    want_out = ob.measure_fock([0, n - 1])
+    post_err = float(np.abs(be.state().ket() - ob.state().data).max())
+    ok = bool(err < 1e-12 and tr_err < 1e-12 and fp_err < 1e-12 and probs_err < 1e-12
+              and np.array_equal(got_out, want_out) and post_err < 1e-12)
     print(json.dumps({"rank": dist.get_rank(), "world": dist.get_world_size(), "err": err,
                       "trace_err": float(tr_err), "fock_prob_err": float(fp_err),
                       "exchanges": int(be.circuit.exchanges), "p2p": bool(be.circuit._p2p), "ok": ok}))
