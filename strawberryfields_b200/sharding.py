@@ -192,8 +192,15 @@ class ShardedCircuit(DeviceCircuit):
             # once, and the streaming kernels are slowest on the last two axes
             # Never evict the innermost axis if it can be avoided: swapping it would cut the exchange
             # into 16*D/p-byte (80 B) runs -- measured 110 GB/s instead of 590 GB/s over NVLink.
+            # The earliest blocked gate must be runnable after the exchange (progress guarantee): the whole
+            # axes that hold ITS modes are never evicted.
             n = self._num_modes
-            cand = list(range(g, n - 1)) if n - 1 - g >= g else list(range(g, n))
+            need = set(ops[order[0]].axes)
+            cand = [p for p in range(g, n) if self._phys[p] not in need]
+            if len(cand) < g:
+                raise L.B200Error("a %d-mode state is too small to shard over %d ranks" % (n, self._world))
+            if len([p for p in cand if p != n - 1]) >= g:
+                cand = [p for p in cand if p != n - 1]
             local = [(next_use.get(self._phys[pos], 1 << 30), pos) for pos in cand]
             local.sort(reverse=True)
             self._exchange(sorted(pos for _, pos in local[:g]))

@@ -14,6 +14,10 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
 def main():
+    if os.environ.get("B200_DUMP_AFTER"):  # debugging aid: where is a rank stuck?
+        import faulthandler
+
+        faulthandler.dump_traceback_later(int(os.environ["B200_DUMP_AFTER"]), exit=True)
     mode = sys.argv[1]          # "host" (gloo + numpy double) or "gpu" (nccl + CUDA kernels)
     n, D = int(sys.argv[2]), int(sys.argv[3])
     from strawberryfields_b200 import circuit, lib
