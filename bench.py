@@ -2,13 +2,18 @@
 """Benchmark of the Fock-backend hot path (BASELINE.json metric: Fock amp-gate updates/s +
 achieved HBM GB/s).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--modes M]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--workload c1|c2|c3|c4] [--modes M] [--fuse fold|tile|off] [--exchange auto|p2p|nccl]
 
 Workload (N = 1): BASELINE config 2 -- 8-mode pure state, cutoff 10 (1e8 complex128
 amplitudes, 1.6 GB), Sgate + Dgate on every mode and a random 8-mode rectangular
 interferometer = 80 gates (8 S + 8 D + 36 R + 28 BS).  A "step" is one pass of the whole
 circuit over the resident state.  One amp-gate update = one stored amplitude passing
 through one gate of the call list (fused or not), so a step is 80 x 1e8 updates.
+Under torchrun (N > 1) the workload is BASELINE config 5: ONE 9-mode state (1e9 amplitudes)
+sharded over the N GPUs ("scaling": "strong"; `--modes 10` gives the 160 GB state on 8 GPUs).
+`--workload c1|c3|c4` run the other BASELINE configs on one GPU (boson sampling, mixed state +
+loss, batched QNN layer).
 
 * ``value``: updates/s with the state resident in HBM, CUDA-event timed, max over ranks.
 * ``e2e``: the same metric through the reference-facing plugin API (``B200FockBackend``:

@@ -89,7 +89,6 @@ class DeviceCircuit:
         self._fuse = fuse if fuse in ("tile", "fold") else ("fold" if fuse else False)
         self._scratch = None
         self._part = None
-        self._norm_out = torch.zeros(2, dtype=torch.float64, device=self.device)
         self._norm_part = torch.zeros(4096, dtype=torch.float64, device=self.device)
         self.reset(pure=pure, cutoff_dim=trunc)
 

@@ -278,7 +278,6 @@ class FakeLib:
             return -2
         lo, mid, hi = stride1 // D, stride0 // (D * stride1), total // (D * stride0)
         pos = [1, 3, 5]
-        letters = "abcdef"
         for b in range(nb):
             st = _c(_addr(state) + 16 * b * sbs, total)
             cur = st.reshape(hi, D, mid, D, lo, D).copy()
@@ -305,7 +304,6 @@ class FakeLib:
             for k in range(3):
                 order[pos[out_perm[k]]] = pos[k]
             st[:] = np.ascontiguousarray(cur.transpose(order)).reshape(-1)
-        del letters
         self.launches += 1
         return 0
 
