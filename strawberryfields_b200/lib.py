@@ -110,15 +110,17 @@ def load(build_if_missing: bool = True):
     global _lib
     if _lib is not None:
         return _lib
-    if build_if_missing:
+    if build_if_missing and not os.path.exists(LIB_PATH):
+        # only a MISSING library is built here (single process, rank 0 of a multi-rank job must build
+        # beforehand); a stale one is rebuilt explicitly with `python -m strawberryfields_b200.build`
         try:
             from . import build as _build
 
-            if _build.needs_build() and os.path.exists(os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")):
+            if os.path.exists(os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")) and \
+                    int(os.environ.get("WORLD_SIZE", "1")) == 1:
                 _build.build()
-        except Exception as exc:  # a stale .so is still better than nothing; a missing one is fatal below
-            if not os.path.exists(LIB_PATH):
-                raise B200Error(f"libb200fock.so is missing and could not be built: {exc}") from exc
+        except Exception as exc:
+            raise B200Error(f"libb200fock.so is missing and could not be built: {exc}") from exc
     if not os.path.exists(LIB_PATH):
         raise B200Error(
             f"{LIB_PATH} not found: build it with `python -m strawberryfields_b200.build` "

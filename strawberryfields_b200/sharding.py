@@ -214,13 +214,20 @@ class ShardedCircuit(DeviceCircuit):
             return False
         ok = True
         peers = None
+        # Every collective below is reached by every rank whatever fails locally (a rank that bailed
+        # out early would leave the others waiting in all_gather_object).
+        shared = None
         try:
             self._bufs.append(self._new(size))
-            shared = []
-            for b in self._bufs:
-                shared.append((b.untyped_storage()._share_cuda_(), b.storage_offset()))
-            everyone = [None] * self._world
-            dist.all_gather_object(everyone, (self.device.index, shared), group=self._pg)
+            shared = [(b.untyped_storage()._share_cuda_(), b.storage_offset()) for b in self._bufs]
+        except Exception as exc:
+            ok = False
+            self._p2p_error = repr(exc)
+        everyone = [None] * self._world
+        dist.all_gather_object(everyone, (self.device.index, shared), group=self._pg)
+        try:
+            if any(sh is None for _, sh in everyone):
+                raise RuntimeError("a peer could not export its buffers")
             peers = [[None] * self._world for _ in range(2)]
             for r, (dev, sh) in enumerate(everyone):
                 for i in range(2):
