@@ -1,0 +1,239 @@
+"""Exchange planning for sharded states (pure host logic, no torch, no device).
+
+A sharded state keeps ``g`` of its ``n`` tensor axes split over the ranks; a gate can only run
+when all its modes sit on whole (local) axes.  One exchange swaps ALL ``g`` sharded axes with
+``g`` local ones (``ShardedCircuit._exchange``), moving (P-1)/P of every shard over NVLink, so
+the number of exchanges is the communication cost of a flush.  This module decides, for a
+queue of gates,
+
+* the order the gates run in (any order that keeps gates sharing a mode in program order),
+* which local modes every exchange evicts,
+* and, for a state that is still the vacuum, which modes start out sharded and which mode
+  lives on the innermost axis (the layout of |0..0> is free).
+
+``greedy`` is the online rule (evict the modes whose next use is farthest away -- Belady);
+``plan`` runs a bounded depth-first search seeded with the greedy answer and never returns
+anything worse.  On the 9- and 10-mode interferometer circuits of BASELINE config 5 over 8
+ranks the search needs 3 exchanges where the greedy rule needs 5 and 4.  The work is bounded
+by a budget of queue sweeps (a few milliseconds of Python) and ``ShardedCircuit`` caches the
+plan per queue structure.
+
+The reference has no distributed path; the gate-order freedom used here
+is the one its ``pu.optimize_circuit`` / DAG utilities express
+(``/root/reference/strawberryfields/program_utils.py:329``): gates on disjoint modes commute.
+"""
+from __future__ import annotations
+
+from itertools import combinations
+
+INNER_PENALTY = 2     # an exchange that evicts the innermost axis moves 16*D/p-byte runs: ~3x slower
+DEFAULT_BUDGET = 2500  # queue sweeps one plan() may spend (~5 us each for a 60-gate queue)
+_FAR = 1 << 30
+
+
+def _mask(modes):
+    m = 0
+    for a in modes:
+        m |= 1 << a
+    return m
+
+
+def sweep(masks, order, sharded):
+    """Run everything runnable: gates (in queue order) whose modes are local and not behind an
+    earlier blocked gate.  ``masks[i]`` / ``sharded`` are mode bit masks.  Returns (run, rest)."""
+    blocked, run, rest = sharded, [], []
+    for i in order:
+        m = masks[i]
+        if m & blocked:
+            blocked |= m
+            rest.append(i)
+        else:
+            run.append(i)
+    return run, rest
+
+
+def _swap(phys, g, T):
+    phys = list(phys)
+    for k in range(g):
+        phys[k], phys[T[k]] = phys[T[k]], phys[k]
+    return phys
+
+
+def _belady(op_axes, order, phys, g):
+    """Positions to evict by the online rule; ``order`` is the blocked remainder of the queue."""
+    n = len(phys)
+    next_use = {}
+    for r, i in enumerate(order):
+        for a in op_axes[i]:
+            next_use.setdefault(a, r)
+    # the earliest blocked gate must be runnable after the exchange (progress guarantee): the whole
+    # axes that hold ITS modes are never evicted; the innermost axis only when nothing else is left
+    need = set(op_axes[order[0]])
+    cand = [p for p in range(g, n) if phys[p] not in need]
+    if len(cand) < g:
+        raise ValueError("a %d-mode state has too few whole axes to exchange %d sharded ones" % (n, g))
+    if len([p for p in cand if p != n - 1]) >= g:
+        cand = [p for p in cand if p != n - 1]
+    far = sorted(((next_use.get(phys[p], _FAR), p) for p in cand), reverse=True)
+    return sorted(p for _, p in far[:g])
+
+
+def greedy(op_axes, phys, g, left=None):
+    """The online plan.  Returns (cost, steps): steps are ``("run", [i, ..])`` /
+    ``("exchange", (evicted modes))``; cost counts exchanges (+ INNER_PENALTY for each one that
+    evicts the innermost axis)."""
+    phys = list(phys)
+    n = len(phys)
+    masks = [_mask(a) for a in op_axes]
+    order = list(range(len(op_axes)))
+    steps, cost = [], 0
+    while True:
+        run, order = sweep(masks, order, _mask(phys[:g]))
+        if left is not None:
+            left[0] -= 1
+        if run:
+            steps.append(("run", run))
+        if not order:
+            return cost, steps
+        T = _belady(op_axes, order, phys, g)
+        cost += 1 + (INNER_PENALTY if n - 1 in T else 0)
+        steps.append(("exchange", tuple(phys[p] for p in T)))
+        phys = _swap(phys, g, T)
+
+
+def search(op_axes, phys, g, left, penalty=INNER_PENALTY, bound=None):
+    """Cheapest plan found by a depth-first search from layout ``phys`` (cost = number of
+    exchanges, plus ``penalty`` for every one that evicts the innermost axis); ``left[0]`` is the
+    remaining sweep budget, shared with the caller.  Returns (cost, steps), or None when nothing
+    cheaper than ``bound`` was found."""
+    n = len(phys)
+    masks = [_mask(a) for a in op_axes]
+    best = [bound if bound is not None else _FAR, None]
+    seen = {}
+
+    def rec(order, phys, cost, trail):
+        run, rest = sweep(masks, order, _mask(phys[:g]))
+        left[0] -= 1
+        if run:
+            trail = trail + [("run", run)]
+        if not rest:
+            if cost < best[0]:
+                best[0], best[1] = cost, trail
+            return
+        if cost + 1 >= best[0] or left[0] <= 0:
+            return
+        key = (tuple(rest), _mask(phys[:g]), phys[n - 1])
+        if seen.get(key, _FAR) <= cost:
+            return
+        seen[key] = cost
+        opts = []
+        for T in combinations(range(g, n), g):
+            c = 1 + (penalty if T[-1] == n - 1 else 0)
+            if cost + c >= best[0]:
+                continue
+            if left[0] <= 0:
+                break
+            left[0] -= 1
+            new = _swap(phys, g, T)
+            r2 = sweep(masks, rest, _mask(new[:g]))[1]
+            if len(r2) < len(rest):  # an exchange that unblocks nothing is never useful
+                opts.append((c, len(r2), T, new))
+        opts.sort()
+        for c, _, T, new in opts:
+            if cost + c < best[0]:
+                rec(rest, new, cost + c, trail + [("exchange", tuple(phys[p] for p in T))])
+
+    rec(list(range(len(op_axes))), list(phys), 0, [])
+    return None if best[1] is None else (best[0], best[1])
+
+
+def exchanges(steps):
+    return sum(1 for s in steps if s[0] == "exchange")
+
+
+def plan(op_axes, phys, g, free_layout=False, budget=DEFAULT_BUDGET):
+    """Plan a flush.  ``op_axes``: modes of every queued gate, in program order; ``phys``: mode on
+    every tensor axis (the first ``g`` are sharded); ``free_layout``: the state is still |0..0>, so
+    the planner may also pick the layout.  Returns ``(phys0, steps)``: the layout to start from
+    (== ``phys`` unless ``free_layout``) and the steps, exchanges given as the tuple of evicted
+    MODES (the ``g`` sharded modes all come in)."""
+    phys = list(phys)
+    n = len(phys)
+    op_axes = [tuple(a) for a in op_axes]
+    if g == 0 or not op_axes:
+        return phys, ([("run", list(range(len(op_axes))))] if op_axes else [])
+    left = [budget if not free_layout else budget // 4]
+    cost, base = greedy(op_axes, phys, g)
+    if cost > 0:
+        found = search(op_axes, phys, g, left, bound=cost)
+        if found:
+            base = found[1]
+    if not free_layout or exchanges(base) == 0:
+        return phys, base
+
+    # ---- vacuum: choose the initially sharded modes, then the innermost mode; the given layout is
+    # kept unless another one saves at least one exchange ----
+    def layout(sh):
+        return list(sh) + [m for m in phys if m not in sh]
+
+    left = [budget - budget // 4]
+    starts = []
+    for sh in combinations(sorted(phys), g):
+        if left[0] <= budget // 3:  # keep at least a third of the budget for the searches
+            break
+        try:
+            starts.append((greedy(op_axes, layout(sh), g, left)[0], sh))
+        except ValueError:
+            continue
+    starts.sort()
+    best = (exchanges(base), None, None)
+    for _, sh in starts[:4]:
+        if left[0] <= 0:
+            break
+        # positions are not final yet: search without the innermost penalty, fix the layout afterwards
+        found = search(op_axes, layout(sh), g, left, penalty=0, bound=best[0])
+        if found is not None:
+            best = (found[0], found[1], sh)
+    if best[1] is None:
+        return phys, base
+    _, steps, sh = best
+    evicted = set(sh)
+    for s in steps:
+        if s[0] == "exchange":
+            evicted.update(s[1])
+    uses = {m: 0 for m in phys}
+    for a in op_axes:
+        for m in a:
+            uses[m] += 1
+    rest = [m for m in phys if m not in sh]
+    # innermost axis: a mode that is never exchanged, the least-used one (the streaming kernels are
+    # slowest on the last axis); everything else keeps ascending order
+    stay = sorted((m for m in rest if m not in evicted), key=lambda m: (-uses[m], m))
+    if stay:
+        last = stay[-1]
+        rest = [m for m in rest if m != last] + [last]
+    return list(sh) + rest, steps
+
+
+def check(op_axes, phys0, g, steps):
+    """Replay a plan on the host and verify it: every gate runs exactly once, on local modes, and
+    gates sharing a mode keep their program order.  Returns the final layout."""
+    phys = list(phys0)
+    done, last_on_mode = set(), {}
+    for s in steps:
+        if s[0] == "run":
+            sharded = set(phys[:g])
+            for i in s[1]:
+                assert i not in done, "gate %d runs twice" % i
+                for m in op_axes[i]:
+                    assert m not in sharded, "gate %d runs on a sharded mode" % i
+                    assert last_on_mode.get(m, -1) < i, "gate %d overtakes a later gate on mode %d" % (i, m)
+                    last_on_mode[m] = i
+                done.add(i)
+        else:
+            pos = {m: p for p, m in enumerate(phys)}
+            T = sorted(pos[m] for m in s[1])
+            assert len(T) == g and T[0] >= g, "exchange must evict %d local modes" % g
+            phys = _swap(phys, g, T)
+    assert done == set(range(len(op_axes))), "gates left over"
+    return phys

@@ -18,9 +18,11 @@ logical mode lives on which physical axis is tracked on the host; nothing is swa
 
 Scheduling.  Gates are queued (as in the single-GPU lazy queue) and, at a flush, executed
 in dependency order preferring gates whose modes are local; when every runnable gate needs
-a sharded mode the exchange brings those modes in and evicts the local modes whose next
-use is farthest away (Belady), so a rectangular interferometer mesh needs only a handful of
-exchanges.
+a sharded mode an exchange brings the sharded modes in.  Which local modes it evicts -- and,
+while the state is still the vacuum, which modes start out sharded -- is decided by
+``exchange_plan.plan``: a bounded search seeded with the online farthest-next-use (Belady)
+rule.  The 9- and 10-mode interferometer circuits need 2 exchanges on 2 or 4 ranks and 3
+on 8 ranks.
 """
 from __future__ import annotations
 
@@ -29,8 +31,12 @@ import torch
 import torch.distributed as dist
 
 from . import lib as L
+from . import exchange_plan as X
 from . import scheduler as S
 from .circuit import DeviceCircuit, _ptr
+
+
+_PLANS = {}  # (queue structure, layout, g, fresh) -> exchange plan: a repeated circuit is planned once
 
 
 def factor_world(P, D):
@@ -136,6 +142,7 @@ class ShardedCircuit(DeviceCircuit):
         self._phys = list(range(self._num_modes))
         self._pos = list(range(self._num_modes))
         self._untouched = set(range(self._num_modes))
+        self._fresh = True  # still |0..0>: the first flush may choose which modes start out sharded
 
     # ------------------------------------------------------------------ queue: everything is deferred
     def _tile_mode(self):
@@ -168,42 +175,35 @@ class ShardedCircuit(DeviceCircuit):
             return
         ops, self._opq = self._opq, []
         self._own()
-        g = self._g
-        order = list(range(len(ops)))
-        while order:
-            blocked, rest = set(), []
-            for i in order:
-                ax = ops[i].axes
-                if not any(a in blocked for a in ax) and all(self._pos[a] >= g for a in ax):
+        # The plan (exchange_plan.py) is a pure function of the queue and the layout, so every rank
+        # derives the same one.  It never evicts the innermost axis if that can be avoided: swapping it
+        # would cut the exchange into 16*D/p-byte (80 B) runs -- measured 110 GB/s instead of 590 GB/s
+        # over NVLink -- and while the state is still |0..0> it may also pick the layout.
+        key = (tuple(op.axes for op in ops), tuple(self._phys), self._g, self._fresh)
+        if key not in _PLANS:
+            if len(_PLANS) >= 64:
+                _PLANS.clear()
+            try:
+                _PLANS[key] = X.plan(key[0], self._phys, self._g, free_layout=self._fresh)
+            except ValueError as exc:
+                raise L.B200Error("%s (%d ranks)" % (exc, self._world)) from exc
+        phys0, steps = _PLANS[key]
+        if phys0 != self._phys:
+            self._set_layout(phys0)
+        self._fresh = False
+        for step in steps:
+            if step[0] == "run":
+                for i in step[1]:
                     self._exec(ops[i])
-                else:
-                    blocked.update(ax)
-                    rest.append(i)
-            order = rest
-            if not order:
-                break
-            # every runnable gate touches a sharded axis: bring all sharded modes in, evict the local
-            # modes whose next use is farthest in the remaining program (Belady)
-            next_use = {}
-            for rank_, i in enumerate(order):
-                for a in ops[i].axes:
-                    next_use.setdefault(a, rank_)
-            # ties: keep the two innermost axes for the residents -- the modes coming in are used at
-            # once, and the streaming kernels are slowest on the last two axes
-            # Never evict the innermost axis if it can be avoided: swapping it would cut the exchange
-            # into 16*D/p-byte (80 B) runs -- measured 110 GB/s instead of 590 GB/s over NVLink.
-            # The earliest blocked gate must be runnable after the exchange (progress guarantee): the whole
-            # axes that hold ITS modes are never evicted.
-            n = self._num_modes
-            need = set(ops[order[0]].axes)
-            cand = [p for p in range(g, n) if self._phys[p] not in need]
-            if len(cand) < g:
-                raise L.B200Error("a %d-mode state is too small to shard over %d ranks" % (n, self._world))
-            if len([p for p in cand if p != n - 1]) >= g:
-                cand = [p for p in cand if p != n - 1]
-            local = [(next_use.get(self._phys[pos], 1 << 30), pos) for pos in cand]
-            local.sort(reverse=True)
-            self._exchange(sorted(pos for _, pos in local[:g]))
+            else:
+                self._exchange(sorted(self._pos[m] for m in step[1]))
+
+    def _set_layout(self, phys):
+        self._phys = list(phys)
+        pos = [0] * len(phys)
+        for p, v in enumerate(phys):
+            pos[v] = p
+        self._pos = pos
 
     # ------------------------------------------------------------------ peer mapping (NVLink P2P)
     def _setup_p2p(self, size):
@@ -318,11 +318,8 @@ class ShardedCircuit(DeviceCircuit):
         phys = list(self._phys)
         for k in range(g):
             phys[k], phys[T[k]] = phys[T[k]], phys[k]
-        self._phys = phys
-        pos = [0] * n
-        for p, v in enumerate(phys):
-            pos[v] = p
-        self._pos = pos
+        self._set_layout(phys)
+        self._fresh = False
         self.exchanges += 1
         self.exchange_bytes += 16 * self._size() * (self._world - 1) // self._world
 
@@ -508,6 +505,7 @@ class ShardedCircuit(DeviceCircuit):
         when the buffers are mapped into the peers)."""
         n = self._num_modes
         assert all(self._pos[m] >= self._g for m in modes)
+        self._fresh = False
         if self._p2p:
             out = self._bufs[1 - self._cur]
         else:

@@ -45,6 +45,9 @@ def main():
     be.begin_circuit(n, cutoff_dim=D, shard=True, exchange=exchange)
     W.run_calls(be, calls + extra)
     st = be.state()
+    from strawberryfields_b200 import sharding
+
+    first_layout = list(next(iter(sharding._PLANS.values()))[0])  # layout the planner chose for |0..0>
     ket = st.ket()
     ob = OracleBackend()
     ob.begin_circuit(n, cutoff_dim=D)
@@ -66,7 +69,8 @@ def main():
               and np.array_equal(got_out, want_out) and post_err < 1e-12)
     print(json.dumps({"rank": dist.get_rank(), "world": dist.get_world_size(), "err": err,
                       "trace_err": float(tr_err), "fock_prob_err": float(fp_err),
-                      "exchanges": int(be.circuit.exchanges), "p2p": bool(be.circuit._p2p), "ok": ok}))
+                      "exchanges": int(be.circuit.exchanges), "p2p": bool(be.circuit._p2p),
+                      "free_layout": bool(first_layout != list(range(n))), "ok": ok}))
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

@@ -54,10 +54,12 @@ def test_factor_world():
         factor_world(2, 7)
 
 
-@pytest.mark.parametrize("world,n,D", [(2, 4, 4), (3, 4, 6), (4, 5, 6)])
+@pytest.mark.parametrize("world,n,D", [(2, 4, 4), (3, 4, 6), (4, 5, 6), (8, 8, 2)])
 def test_sharded_circuit_matches_oracle_gloo(world, n, D):
     lines = _run("host", world, n, D)
     assert lines[0]["exchanges"] >= 1  # the circuit touches sharded modes: at least one all-to-all
+    if world == 8:  # three sharded axes: the planner starts the vacuum from a layout of its own choice
+        assert lines[0]["free_layout"]
 
 
 @pytest.mark.gpu
