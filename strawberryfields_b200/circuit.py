@@ -957,6 +957,41 @@ class DeviceCircuit:
         self._gather(self._buf, self._buf, out, oa, red, flags=L.FLAG_CONJ_B)
         return out.view(B, -1)
 
+    def product_overlap_device(self, vectors):
+        """<v_0 x .. x v_{n-1}|psi> (pure) or <v|rho|v> (mixed) for one [D] vector per mode, as a device
+        complex128 tensor [B] -- the contraction behind ``fidelity_coherent`` (states.py:687-728),
+        done one mode at a time on the resident state instead of against a D^n product vector built
+        on the host: the first launch reads the state once, every later one a D-th of the previous."""
+        self._flush()
+        n, D, B = self._num_modes, self._trunc, self._B
+        cur = self._buf
+        per = self._size()
+        # strides of the modes still present in ``cur`` (one per mode for kets, (ket, bra) for dms)
+        strides = {m: [self._stride(ax) for ax in self._mode_axes(m)] for m in range(n)}
+        for m in sorted(range(n), key=lambda q: strides[q][0]):  # innermost first: contiguous reads
+            v = np.asarray(vectors[m], dtype=C128).reshape(D)
+            if self._pure:
+                w, red, flags = v, [(D, strides[m][0], 1)], L.FLAG_CONJ_B
+            else:
+                w, red, flags = np.multiply.outer(v.conj(), v), [(D, strides[m][0], D), (D, strides[m][1], 1)], 0
+            w = torch.from_numpy(np.ascontiguousarray(w)).to(self.device)
+            del strides[m]
+            rest = sorted(strides, key=lambda q: -strides[q][0])  # outermost first in the new tensor
+            width = len(self._mode_axes(0))
+            new_per = D ** (width * len(rest))
+            out = self._new(B * new_per)
+            oa = [(B, per, 0, new_per)] if B > 1 else []
+            new_strides, k = {}, width * len(rest)
+            for q in rest:
+                new_strides[q] = []
+                for st in strides[q]:
+                    k -= 1
+                    oa.append((D, st, 0, D ** k))
+                    new_strides[q].append(D ** k)
+            self._gather(cur, w, out, oa, red, flags=flags)
+            cur, per, strides = out, new_per, new_strides
+        return cur
+
     # ------------------------------------------------------------------ Fock measurement (circuit.py:623-711)
     def _project_reset(self, modes, values):
         """|0..0><x| on ``modes`` (ops.py:179-198), out of place."""

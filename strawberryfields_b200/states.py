@@ -139,6 +139,81 @@ class _FockStateMixin:
     def fidelity_vacuum(self, **kwargs):
         return self.fock_prob([0] * self._modes)
 
+    def fidelity_coherent(self, alpha_list, **kwargs):
+        """|<alpha|psi>|^2 / <alpha|rho|alpha> (states.py:687-728), contracted on the device."""
+        if not hasattr(alpha_list, "__len__"):
+            alpha_list = [alpha_list]
+        if len(alpha_list) != self._modes:
+            raise ValueError("The number of alpha values must match the number of modes.")
+        ns = np.arange(self._cutoff)
+        sqrt_fact = np.sqrt(np.cumprod(np.concatenate([[1.0], ns[1:]])))
+        vecs = [np.exp(-0.5 * np.abs(a) ** 2) * np.asarray(a, dtype=complex) ** ns / sqrt_fact for a in alpha_list]
+        ov = self._view.product_overlap_device(vecs).cpu().numpy()
+        res = np.abs(ov) ** 2 if self._pure else ov.real
+        return res if self._batched else res[0]
+
+    def diagonal_expectation(self, modes, values):
+        """<prod_k f(n_k)> for an operator diagonal in the number basis (states.py:920-945): the
+        joint photon-number distribution of ``modes`` is reduced on the device (D^k doubles come
+        back), never the state."""
+        modes = list(modes)
+        if len(modes) != len(set(modes)):
+            raise ValueError("There can be no duplicates in the modes specified.")
+        values = np.asarray(values)
+        ps = self._view.marginal_probs_device(sorted(modes)).cpu().numpy()
+        ps = ps.reshape([ps.shape[0]] + [self._cutoff] * len(modes))
+        for _ in modes:
+            ps = np.tensordot(ps, values, axes=([1], [0]))
+        return ps if self._batched else float(ps[0])
+
+    def number_expectation(self, modes):
+        values = np.arange(self._cutoff)
+        mean = self.diagonal_expectation(modes, values)
+        var = self.diagonal_expectation(modes, values ** 2) - mean ** 2
+        return mean, var
+
+    def parity_expectation(self, modes):
+        return self.diagonal_expectation(modes, (-1) ** np.arange(self._cutoff))
+
+    def quad_expectation(self, mode, phi=0, **kwargs):
+        """Mean and variance of x_phi on one mode (states.py:787-804) from its device-reduced
+        density matrix; the ladder operators are built 5 levels above the cutoff and truncated, as
+        the reference does, so x_phi^2 has the reference's boundary terms."""
+        D = self._cutoff
+        a = np.diag(np.sqrt(np.arange(1, D + 5)), 1)
+        x = np.sqrt(self._hbar / 2) * (a + a.T)
+        p = -1j * np.sqrt(self._hbar / 2) * (a - a.T)
+        xphi = np.cos(phi) * x + np.sin(phi) * p
+        xphisq = (xphi @ xphi)[:D, :D]
+        xphi = xphi[:D, :D]
+        rho = self.reduced_dm([mode])
+        mean = np.einsum("ij,...ji->...", xphi, rho).real
+        var = np.einsum("ij,...ji->...", xphisq, rho).real - mean ** 2
+        return mean, var
+
+    def wigner(self, mode, xvec, pvec):
+        """Discretised Wigner function of one mode, [len(pvec), len(xvec)] like the reference's
+        (states.py:730-785), from the device-reduced density matrix:
+        W = sum_mn rho[m, n] W_mn with the |m><n| transforms generated by the ladder recurrences
+        W_0n = 2A W_0,n-1 / sqrt(n),  W_mn = (2A* W_m-1,n - sqrt(n) W_m-1,n-1) / sqrt(m)."""
+        if self._batched:
+            raise NotImplementedError("wigner is not available for batched states")
+        D = self._cutoff
+        rho = self.reduced_dm([mode])
+        Q, P = np.meshgrid(xvec, pvec)
+        A = (Q + 1j * P) / (2 * np.sqrt(self._hbar / 2))
+        prev = [np.exp(-2.0 * np.abs(A) ** 2) / np.pi + 0j]
+        for n in range(1, D):
+            prev.append(2.0 * A * prev[n - 1] / np.sqrt(n))
+        W = sum((rho[0, n] * prev[n]).real * (1 if n == 0 else 2) for n in range(D))
+        for m in range(1, D):  # prev[n] = W_{m-1,n} for n >= m-1; the lower triangle follows by symmetry
+            row = [None] * D
+            for n in range(m, D):
+                row[n] = (2 * np.conj(A) * prev[n] - np.sqrt(n) * prev[n - 1]) / np.sqrt(m)
+                W = W + (rho[m, n] * row[n]).real * (1 if n == m else 2)
+            prev = row
+        return W / self._hbar
+
     def __repr__(self):
         return "<B200FockState: num_modes={}, cutoff={}, pure={}, hbar={}>".format(
             self._modes, self._cutoff, self._pure, self._hbar)

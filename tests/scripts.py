@@ -224,3 +224,39 @@ def all_scripts():
         measure_postselect(6, True),
         measure_postselect(5, False),
     ]
+
+
+# ---------------------------------------------------------------------------
+# Observables of the state object (reference backends/states.py:657-985)
+def observable_scripts():
+    """A pure 3-mode state, a mixed one (single-mode preparations mix the reference state,
+    SURVEY F7) and a lossy 2-mode state at the BASELINE cutoff."""
+    lossy = loss_and_measure(2, 10)
+    lossy = ("lossy_n2_d10", lossy[1], lossy[2], lossy[3],
+             [c for c in lossy[4] if c[0] not in ("measure_fock", "seed")])
+    return [every_gate(3, 6, True, seed=13, prep=False), every_gate(3, 4, False), lossy]
+
+
+def observable_cases(script):
+    """(key, method, args) evaluated on the final state of ``script``."""
+    n = script[1]
+    xs = np.linspace(-2.5, 2.5, 7)
+    ps = np.linspace(-2.0, 2.0, 5)
+    cases = [("fidelity_vacuum", "fidelity_vacuum", ())]
+    alphas = [0.3 * np.exp(0.7j * (m + 1)) for m in range(n)]
+    cases.append(("fidelity_coherent", "fidelity_coherent", (alphas,)))
+    cases.append(("fidelity_coherent_0", "fidelity_coherent", ([0.0] * n,)))
+    for m in range(n):
+        cases.append((f"mean_photon_{m}", "mean_photon", (m,)))
+        cases.append((f"quad_x_{m}", "quad_expectation", (m, 0.0)))
+        cases.append((f"quad_phi_{m}", "quad_expectation", (m, 0.4 + m)))
+        cases.append((f"wigner_{m}", "wigner", (m, xs, ps)))
+        cases.append((f"number_{m}", "number_expectation", ([m],)))
+        cases.append((f"parity_{m}", "parity_expectation", ([m],)))
+    cases.append(("number_01", "number_expectation", ([0, 1],)))
+    cases.append(("number_10", "number_expectation", ([1, 0],)))
+    cases.append(("parity_all", "parity_expectation", (list(range(n)),)))
+    if n > 2:
+        cases.append(("number_02", "number_expectation", ([0, 2],)))
+        cases.append(("parity_21", "parity_expectation", ([2, 1],)))
+    return cases
