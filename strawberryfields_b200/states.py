@@ -191,6 +191,62 @@ class _FockStateMixin:
         var = np.einsum("ij,...ji->...", xphisq, rho).real - mean ** 2
         return mean, var
 
+    def poly_quad_expectation(self, A, d=None, k=0, phi=0, **kwargs):
+        """Mean and variance of P = r^T A r + r^T d + k with r = (x_1..x_N, p_1..p_N)
+        (states.py:806-918).  Only the modes P acts on are kept: their reduced density matrix comes
+        from the device, the operator is built on the host one level above the cutoff (as the
+        reference does), squared there and truncated."""
+        N, D = self._modes, self._cutoff
+        if A is None:
+            A = np.zeros([2 * N, 2 * N])
+        A = np.asarray(A)
+        if A.shape != (2 * N, 2 * N):
+            raise ValueError("Matrix of quadratic coefficients A must be of size 2Nx2N.")
+        if not np.allclose(A.T, A):
+            raise ValueError("Matrix of quadratic coefficients A must be symmetric.")
+        d = np.zeros([2 * N]) if d is None else np.asarray(d)
+        if d.shape != (2 * N,):
+            raise ValueError("Vector of linear coefficients d must be of length 2N.")
+        if self._batched:
+            raise NotImplementedError("poly_quad_expectation is not available for batched states")
+        modes = sorted({int(i) % N for i in A.nonzero()[0]} | {int(i) % N for i in d.nonzero()[0]})
+        if not modes:
+            return k, 0.0
+        m, dim = len(modes), D + 1
+        a = np.diag(np.sqrt(np.arange(1, dim)), 1)
+        x0 = np.sqrt(self._hbar / 2) * (a + a.T)
+        p0 = -1j * np.sqrt(self._hbar / 2) * (a - a.T)
+        x1 = np.cos(phi) * x0 + np.sin(phi) * p0   # x_phi, as in quad_expectation
+        p1 = -np.sin(phi) * x0 + np.cos(phi) * p0  # its conjugate quadrature
+
+        def on_mode(op, j):
+            out = np.ones((1, 1), dtype=complex)
+            for q in range(m):
+                out = np.kron(out, op if q == j else np.eye(dim))
+            return out
+
+        R = [on_mode(x1, j) for j in range(m)] + [on_mode(p1, j) for j in range(m)]
+        rows = modes + [N + q for q in modes]
+        Ar, dr = A[np.ix_(rows, rows)], d[rows]
+        P = k * np.eye(dim ** m, dtype=complex)
+        for i in range(2 * m):
+            if dr[i] != 0:
+                P = P + dr[i] * R[i]
+            for j in range(2 * m):
+                if Ar[i, j] != 0:
+                    P = P + Ar[i, j] * (R[i] @ R[j])
+        Psq = P @ P
+
+        def cut(M):
+            sl = tuple([slice(0, D)] * (2 * m))
+            return M.reshape([dim] * (2 * m))[sl].reshape(D ** m, D ** m)
+
+        rho = self.reduced_dm(modes)
+        rho = rho.transpose(list(range(0, 2 * m, 2)) + list(range(1, 2 * m, 2))).reshape(D ** m, D ** m)
+        mean = np.trace(cut(P) @ rho).real
+        var = np.trace(cut(Psq) @ rho).real - mean ** 2
+        return mean, var
+
     def wigner(self, mode, xvec, pvec):
         """Discretised Wigner function of one mode, [len(pvec), len(xvec)] like the reference's
         (states.py:730-785), from the device-reduced density matrix:

@@ -259,4 +259,17 @@ def observable_cases(script):
     if n > 2:
         cases.append(("number_02", "number_expectation", ([0, 2],)))
         cases.append(("parity_21", "parity_expectation", ([2, 1],)))
+    # polynomials of quadratures: all modes, a mode subset (only modes 0 and n-1 appear), linear only
+    rs = _rng(21)
+    A = rs.randn(2 * n, 2 * n)
+    A = 0.1 * (A + A.T)
+    d = 0.3 * rs.randn(2 * n)
+    cases.append(("polyquad_full", "poly_quad_expectation", (A, d, 0.3, 0.0)))
+    cases.append(("polyquad_full_phi", "poly_quad_expectation", (A, d, 0.0, 0.37)))
+    keep = [0, n - 1, n, 2 * n - 1]
+    As, ds = np.zeros_like(A), np.zeros_like(d)
+    As[np.ix_(keep, keep)] = A[np.ix_(keep, keep)]
+    ds[keep] = d[keep]
+    cases.append(("polyquad_subset", "poly_quad_expectation", (As, ds, -0.2, 0.9)))
+    cases.append(("polyquad_linear", "poly_quad_expectation", (None, d, 0.0, 0.0)))
     return cases

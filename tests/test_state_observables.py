@@ -1,6 +1,6 @@
 """Observables of the state object: ``fidelity_coherent``, ``mean_photon``,
-``quad_expectation``, ``wigner``, ``number_expectation``, ``parity_expectation`` computed from
-device reductions of the resident state.
+``quad_expectation``, ``poly_quad_expectation``, ``wigner``, ``number_expectation``,
+``parity_expectation`` computed from device reductions of the resident state.
 
 * tests/golden/ref_observables.json holds what the UNMODIFIED reference ``BaseFockState``
   returned (written by oracle/make_golden_observables.py in the build container);
@@ -37,9 +37,10 @@ def backend(request, monkeypatch):
     return B200FockBackend
 
 
-def _values(st, script):
+def _values(st, script, skip=()):
     return {key: np.asarray(getattr(st, method)(*args), dtype=np.float64)
-            for key, method, args in scripts.observable_cases(script)}
+            for key, method, args in scripts.observable_cases(script)
+            if hasattr(st, method) and method not in skip}
 
 
 @pytest.mark.parametrize("script", scripts.observable_scripts(), ids=lambda s: s[0])
@@ -47,8 +48,8 @@ def test_oracle_matches_reference(script, golden):
     _, st = scripts.run_script(OracleBackend(), script)
     got = _values(st, script)
     want = golden[script[0]]
-    assert set(got) == set(want)
-    for key in want:
+    assert set(got) == {k for k in want if not k.startswith("polyquad")}  # polyquad: fixture-pinned only
+    for key in got:
         assert np.abs(got[key] - np.asarray(want[key])).max() < TOL, key
 
 
@@ -63,9 +64,12 @@ def test_b200_matches_reference_and_oracle(script, strict, backend, golden):
     _, ost = scripts.run_script(OracleBackend(), script)
     want_o = _values(ost, script)
     want_r = golden[script[0]]
+    assert set(got) == set(want_r)
     for key in want_r:
-        assert np.abs(got[key] - np.asarray(want_r[key])).max() < TOL, key
-        assert np.abs(got[key] - want_o[key]).max() < TOL, key
+        scale = max(1.0, np.abs(np.asarray(want_r[key])).max())  # polyquad variances are O(100)
+        assert np.abs(got[key] - np.asarray(want_r[key])).max() < TOL * scale, key
+        if key in want_o:
+            assert np.abs(got[key] - want_o[key]).max() < TOL, key
 
 
 def test_after_tile_permutation(backend):
@@ -79,7 +83,7 @@ def test_after_tile_permutation(backend):
         for method, args, kwargs in script[4]:
             getattr(be, method)(*args, **kwargs)
         st = be.state()
-        vals.append(_values(st, script))
+        vals.append(_values(st, script, skip=("poly_quad_expectation",)))  # host-only algebra, slow at 4 modes
     for key in vals[0]:
         assert np.abs(vals[0][key] - vals[1][key]).max() < TOL, key
 
