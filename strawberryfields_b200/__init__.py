@@ -11,6 +11,7 @@ or stand-alone through the same backend API (``B200FockBackend``).  All state up
 are hand-written CUDA kernels in ``libb200fock.so`` (C ABI: ``include/b200fock.h``);
 there is no CPU fallback.
 """
+from .autodiff import TorchCircuit  # noqa: F401
 from .backend import B200FockBackend, register  # noqa: F401
 from .circuit import DeviceCircuit, DeviceParams  # noqa: F401
 from .states import B200FockState  # noqa: F401
