@@ -346,3 +346,60 @@ class _CircuitFn(torch.autograd.Function):
             if k > first:  # nothing before the first differentiable gate needs lambda
                 prog._apply(lam, name, modes, prog._table(name, p, prog.cutoff), adjoint=True)
         return (None,) + tuple(grads)
+
+
+# ---------------------------------------------------------------------------------------------
+# CV quantum neural network layers -- the parameter layout of
+# /root/reference/examples/quantum_neural_network.py:14-85 (BASELINE config 4)
+def qnn_interferometer_size(N):
+    return N * (N - 1) + max(1, N - 1)
+
+
+def qnn_layer_size(N):
+    return 2 * qnn_interferometer_size(N) + 4 * N
+
+
+def qnn_interferometer(prog, params, modes):
+    """Rectangular beamsplitter array of depth N on ``modes`` followed by N - 1 rotations;
+    ``params`` = N(N-1)/2 angles, N(N-1)/2 phases, max(1, N-1) rotation angles."""
+    N = len(modes)
+    half = N * (N - 1) // 2
+    theta, phi, rphi = params[:half], params[half:2 * half], params[2 * half:]
+    if N == 1:
+        prog.rotation(rphi[0], modes[0])
+        return
+    n = 0
+    for l in range(N):
+        for k in range(N - 1):
+            if (l + k) % 2 != 1:
+                prog.beamsplitter(theta[n], phi[n], modes[k], modes[k + 1])
+                n += 1
+    for i in range(max(1, N - 1)):
+        prog.rotation(rphi[i], modes[i])
+
+
+def qnn_layer(prog, params, modes=None):
+    """One layer: interferometer, squeezers, interferometer, displacements, Kerr gates.  ``params``
+    is a 1-D tensor (or a [size, batch] tensor for per-entry weights) of ``qnn_layer_size(N)`` rows."""
+    modes = list(range(prog.num_modes)) if modes is None else list(modes)
+    N = len(modes)
+    M = qnn_interferometer_size(N)
+    if len(params) != qnn_layer_size(N):
+        raise ValueError("a %d-mode layer takes %d parameters" % (N, qnn_layer_size(N)))
+    qnn_interferometer(prog, params[:M], modes)
+    for i in range(N):
+        prog.squeeze(params[M + i], 0.0, modes[i])
+    qnn_interferometer(prog, params[M + N:2 * M + N], modes)
+    for i in range(N):
+        prog.displacement(params[2 * M + N + i], params[2 * M + 2 * N + i], modes[i])
+        prog.kerr_interaction(params[2 * M + 3 * N + i], modes[i])
+
+
+def qnn_init_weights(N, layers, active_sd=0.0001, passive_sd=0.1, generator=None, device=None):
+    """[layers, qnn_layer_size(N)] float64 weights: N(0, passive_sd) for angles and phases,
+    N(0, active_sd) for squeezing, displacement and Kerr magnitudes."""
+    M = qnn_interferometer_size(N)
+    sd = torch.tensor([passive_sd] * M + [active_sd] * N + [passive_sd] * M + [active_sd] * N
+                      + [passive_sd] * N + [active_sd] * N, dtype=torch.float64)
+    w = torch.randn(layers, qnn_layer_size(N), dtype=torch.float64, generator=generator) * sd
+    return w.to(device) if device is not None else w

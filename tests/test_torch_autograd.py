@@ -209,6 +209,46 @@ def test_training_step_reduces_loss(make):
     assert fidelity().item() > first + 0.05
 
 
+def test_qnn_layers_batched_weights(make):
+    """BASELINE config 4's shape at reduced size: QNN layers (examples/quantum_neural_network.py:14-85)
+    with per-entry weights; forward equals the oracle entry by entry, gradients equal finite differences."""
+    from strawberryfields_b200.autodiff import qnn_init_weights, qnn_layer, qnn_layer_size
+
+    N, D, B, layers = 3, 4, 2, 2
+    gen = torch.Generator().manual_seed(1)
+    w0 = torch.stack([qnn_init_weights(N, layers, active_sd=0.05, generator=gen) for _ in range(B)], dim=-1)
+    assert w0.shape == (layers, qnn_layer_size(N), B)
+
+    def run(w):
+        prog = make(N, D, batch_size=B)
+        for k in range(layers):
+            qnn_layer(prog, w[k])
+        return prog.ket()
+
+    w = w0.clone().requires_grad_(True)
+    ket = run(w)
+    for b in range(B):
+        ob = OracleBackend()
+        ob.begin_circuit(N, cutoff_dim=D)
+        for k in range(layers):
+            qnn_layer(ob, [float(x) for x in w0[k, :, b]], modes=list(range(N)))
+        assert np.abs(ket[b].detach().cpu().numpy() - ob.state().data).max() < TOL
+    loss = sum(loss_of(ket[b]) * (b + 1) for b in range(B))
+    loss.backward()
+    h = 1e-6
+    rng = np.random.RandomState(0)
+    for _ in range(6):
+        k, i, b = rng.randint(layers), rng.randint(qnn_layer_size(N)), rng.randint(B)
+        vals = []
+        for s in (+1, -1):
+            x = w0.clone()
+            x[k, i, b] += s * h
+            with torch.no_grad():
+                kk = run(x)
+                vals.append(sum(loss_of(kk[c]).item() * (c + 1) for c in range(B)))
+        assert abs(w.grad[k, i, b].item() - (vals[0] - vals[1]) / (2 * h)) < 1e-7, (k, i, b)
+
+
 def test_constant_prefix_and_second_backward(make):
     """Gates before the first differentiable one keep no checkpoint; a second backward pass over the
     same graph is refused (the checkpoints are consumed)."""
