@@ -4,6 +4,7 @@ achieved HBM GB/s).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
                     [--workload c1|c2|c3|c4] [--modes M] [--fuse fold|tile|off] [--exchange auto|p2p|nccl]
+                    [--from-vacuum]
 
 Workload (N = 1): BASELINE config 2 -- 8-mode pure state, cutoff 10 (1e8 complex128
 amplitudes, 1.6 GB), Sgate + Dgate on every mode and a random 8-mode rectangular
@@ -280,11 +281,23 @@ def b200_arm(args):
 
     # ---- device-resident leg: `value` ---------------------------------------------------
     fuse = {"tile": "tile", "fold": "fold", "off": False}[args.fuse]
+    # --from-vacuum: every step is a whole program run -- reset to |0..0>, then the gates -- with the
+    # lazy-vacuum option (modes stay product factors until a two-mode gate needs them).
+    # Default: the gates are applied to whatever state the previous step left (a generic dense state),
+    # i.e. the steady-state cost of the kernels alone.
+    if args.from_vacuum and not sharded and args.workload != "c3":
+        shard_kw = dict(shard_kw, lazy_vacuum=True)
+
+    def one_step(b):
+        if args.from_vacuum:
+            b.reset(pure=args.workload != "c3")
+        W.run_calls(b, calls)
+        b.circuit._flush()
+
     be = B200FockBackend()
     be.begin_circuit(n_modes, cutoff_dim=D, fuse=fuse, **shard_kw)
     for _ in range(args.warmup):
-        W.run_calls(be, calls)
-        be.circuit._flush()
+        one_step(be)
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
@@ -292,8 +305,7 @@ def b200_arm(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        W.run_calls(be, calls)
-        be.circuit._flush()
+        one_step(be)
     e1.record()
     barrier()
     launches = int(handle.b200_launch_count())
@@ -308,8 +320,7 @@ def b200_arm(args):
     # ---- roofline leg: per-launch CUDA events on one more step ------------------------------
     prof = []
     be.circuit.profile = prof
-    W.run_calls(be, calls)
-    be.circuit._flush()
+    one_step(be)
     torch.cuda.synchronize()
     be.circuit.profile = None
     by_tag = {}
@@ -336,7 +347,7 @@ def b200_arm(args):
         "share_of_step_time": dom_time / max(sum(g[1] for g in groups.values()), 1e-12),
         "frac": achieved / peak, "traffic": ncu_traffic(dom_kernel, local_elements), "peak_source": peak_src,
         "launches_per_step": dom_n, "avg_launch_ms": dom_time / max(dom_n, 1) * 1e3,
-        "algorithmic_bytes_per_launch": 32 * local_elements,
+        "algorithmic_bytes_per_launch": dom_bytes / max(dom_n, 1),
         "frac_of_nominal_8TBs": achieved / 8000.0,
         "by_pass": {tag: {"launches": v[2], "GBps": v[0] / v[1] / 1e9} for tag, v in sorted(by_tag.items())},
     }
@@ -419,9 +430,11 @@ def b200_arm(args):
                       % (local_elements * 16 / 1e9),
                 "passes_per_step": sum(v[2] for v in by_tag.values()),
                 "gate_queue": args.fuse,
+                "state_at_step_start": ("vacuum (reset inside the timed step, lazy-vacuum factors)"
+                                        if args.from_vacuum else "dense state left by the previous step"),
             },
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
-            "hbm_GBps_per_gpu_whole_step": 32 * local_elements * sum(v[2] for v in by_tag.values()) * args.steps
+            "hbm_GBps_per_gpu_whole_step": sum(v[0] for v in by_tag.values()) * args.steps
                                            / (ms_total * 1e-3) / 1e9,
             "circuit_ms": ms_total / args.steps,
         }
@@ -463,7 +476,11 @@ def main():
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
                     help="multi-GPU axis exchange: peer-memory pull kernel or pack + NCCL all-to-all + unpack")
     ap.add_argument("--fuse", default="fold", choices=["tile", "fold", "off"],
-                    help="gate queue: tile passes (default), diagonal folding only, or one pass per gate")
+                    help="gate queue: diagonal / same-mode folding (default), + multi-gate tile passes, "
+                         "or one pass per gate")
+    ap.add_argument("--from-vacuum", action="store_true",
+                    help="every step resets to vacuum first and uses the lazy-vacuum option (not yet the default: "
+                         "unmeasured in round 1)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

@@ -143,6 +143,8 @@ class B200FockBackend(_Base):
             "strict_purity": bool(kwargs.get("strict_purity", False)),
             "fuse": kwargs.get("fuse", True),  # True|"fold": gate folding; "tile": + multi-gate tile passes; False: off
             "device": kwargs.get("device", None),
+            # keep modes that no two-mode gate has touched yet as product factors; off by default
+            "lazy_vacuum": bool(kwargs.get("lazy_vacuum", False)),
         }
         self._init_modes = num_subsystems
         shard = kwargs.get("shard", False)

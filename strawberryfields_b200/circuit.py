@@ -63,7 +63,7 @@ class DeviceCircuit:
     """GPU mirror of ``fockbackend.circuit.Circuit``."""
 
     def __init__(self, num, trunc, pure=True, batch_size=None, device=None, strict_purity=False,
-                 fuse=True):
+                 fuse=True, lazy_vacuum=False):
         if num < 0:
             raise ValueError("Number of modes must be non-negative -- got {}".format(num))
         if trunc <= 0:
@@ -87,6 +87,10 @@ class DeviceCircuit:
         # True / "fold": fold diagonal and same-mode gates, one streaming pass per remaining gate (default);
         # "tile": additionally group gates into multi-gate tile passes (scheduler.py); False: one pass per gate
         self._fuse = fuse if fuse in ("tile", "fold") else ("fold" if fuse else False)
+        # lazy vacuum (pure states, fuse="fold"): a mode that no two-mode gate has touched yet is a
+        # product factor (its pending single-mode operator applied to |0>); the device tensor only
+        # spans the modes that have been entangled so far and grows by one axis when a gate needs it
+        self._lazy_opt = bool(lazy_vacuum)
         self._scratch = None
         self._part = None
         self._norm_part = torch.zeros(4096, dtype=torch.float64, device=self.device)
@@ -102,12 +106,13 @@ class DeviceCircuit:
         return self._num_modes if self._pure else 2 * self._num_modes
 
     def _size(self):
-        """elements per batch entry"""
-        return self._trunc ** self._axes()
+        """elements per batch entry of the device tensor (all axes, unless lazy-vacuum modes are
+        still outside it)"""
+        return self._trunc ** len(self._phys)
 
     def _stride(self, axis):
         """element stride of (virtual) tensor axis ``axis`` in the current physical layout"""
-        return self._trunc ** (len(self._pos) - 1 - self._pos[axis])
+        return self._trunc ** (len(self._phys) - 1 - self._pos[axis])
 
     def _canon_stride(self, axis):
         return self._trunc ** (self._axes() - 1 - axis)
@@ -117,9 +122,10 @@ class DeviceCircuit:
         permute axes (scheduler.py); everything that reads the state goes through _stride()."""
         self._phys = list(range(self._axes()))
         self._pos = list(range(self._axes()))
+        self._inactive = set()
 
     def _is_canonical(self):
-        return all(p == v for p, v in enumerate(self._phys))
+        return len(self._phys) == self._axes() and all(p == v for p, v in enumerate(self._phys))
 
     def _canonicalize(self):
         """Restore the canonical axis order (one out-of-place strided copy)."""
@@ -168,6 +174,7 @@ class DeviceCircuit:
         snap._pending = {}
         snap._opq = []
         snap._untouched = set()
+        snap._inactive = set()
         snap._scratch = None
         snap._part = None
         snap._norm_part = torch.zeros(4096, dtype=torch.float64, device=self.device)
@@ -231,13 +238,20 @@ class DeviceCircuit:
         self._scratch = None
         self._buf = None
         self._shared = False
+        self._pending = {}
+        self._opq = []
+        self._untouched = set(range(self._num_modes))
+        if self._lazy_opt and self._pure and self._fuse == "fold" and self._num_modes > 0:
+            # nothing is entangled yet: the device tensor has no axes (one amplitude, 1, per batch entry)
+            self._phys = []
+            self._pos = [None] * self._num_modes
+            self._inactive = set(range(self._num_modes))
+            self._buf = torch.ones(self._B, dtype=torch.complex128, device=self.device)
+            return
+        self._set_identity_layout()
         per = self._size()
         self._buf = self._new(self._B * per)
         self._vacuum(self._buf, per)
-        self._pending = {}
-        self._opq = []
-        self._set_identity_layout()
-        self._untouched = set(range(self._num_modes))
 
     # ------------------------------------------------------------------ gate tables
     def _params(self, *ps):
@@ -314,7 +328,7 @@ class DeviceCircuit:
     def _k_gate1(self, U, axis, conj):
         self._own()
         D, B = self._trunc, self._B
-        naxes = self._axes()
+        naxes = len(self._phys)
         nb = U.shape[0]
         pos = self._pos[axis]
         inner = self._stride(axis)
@@ -326,7 +340,7 @@ class DeviceCircuit:
         self._own()
         D, B = self._trunc, self._B
         nb = G.shape[0]
-        naxes = self._axes()
+        naxes = len(self._phys)
         # the C side routes pair gates with an axis of stride 1 to the staged kernel (k_apply_inner)
         staged = min(self._stride(ax1), self._stride(ax2)) == 1 and 2 <= D <= L.MAX_FAST_CUTOFF
         self._pass("%s/rule%d/axes%d,%d" % ("inner2" if staged else "gate2", rule, naxes - 1 - self._pos[ax1],
@@ -514,10 +528,40 @@ class DeviceCircuit:
             L.call("b200_fold_diag_gate1", D, nb, _ptr(P), None, _ptr(self._expand(d, nb)), self._stream())
             self._pending[mode] = ("dense", P)
 
+    def _activate(self, modes):
+        """Lazy vacuum: bring the still-factored modes among ``modes`` into the device tensor.  Such
+        a mode is |0> with (at most) one pending single-mode operator P, i.e. the factor P|0> = column
+        0 of P; the tensor grows by one (outermost) axis with one outer-product launch that WRITES the
+        new tensor once -- instead of a read + write pass over the full-size state per such gate."""
+        D, B = self._trunc, self._B
+        for m in modes:
+            if m not in self._inactive:
+                continue
+            pend = self._pending.pop(m, None)
+            if pend is None or pend[0] == "diag":
+                v = torch.zeros(1 if pend is None else pend[1].shape[0], D, dtype=torch.complex128,
+                                device=self.device)
+                v[:, 0] = 1.0 if pend is None else pend[1][:, 0]
+            else:
+                v = pend[1][:, :, 0].contiguous()
+            old_per = self._size()
+            out = self._new(B * old_per * D)
+            oa = [(B, old_per, D if v.shape[0] > 1 else 0, old_per * D)] if B > 1 else []
+            oa += [(D, 0, 1, old_per), (old_per, 1, 0, 1)]
+            self._gather(self._buf, v, out, oa)
+            self._buf, self._shared, self._scratch = out, False, None
+            self._inactive.discard(m)
+            self._phys = [m] + self._phys
+            for p, ax in enumerate(self._phys):
+                self._pos[ax] = p
+
     def _flush(self, modes=None):
         """Move the pending single-mode operators of ``modes`` (default: all) out of the fold
         stage.  A full flush (``modes is None``) also runs every queued tile pass, after which
         the device buffer holds the up-to-date state."""
+        if self._inactive:
+            # descending: every activation adds the outermost axis, so a fresh vacuum ends up canonical
+            self._activate(sorted(self._inactive if modes is None else modes, reverse=True))
         if self._pending:
             keys = sorted(self._pending) if modes is None else [m for m in modes if m in self._pending]
             diags = []
@@ -536,6 +580,8 @@ class DeviceCircuit:
         """Two-mode gate: pending diagonals on its modes are folded into the table,
         pending dense operators are flushed first."""
         self._touch(m1, m2)
+        if self._inactive:
+            self._activate(sorted((m1, m2), reverse=True))
         D = self._trunc
         pre = [None, None]
         for i, m in enumerate((m1, m2)):
@@ -593,6 +639,8 @@ class DeviceCircuit:
     def cross_kerr_interaction(self, kappa, mode1, mode2):
         # diagonal in both modes: commutes with pending diagonals, not with pending dense gates
         self._touch(mode1, mode2)
+        if self._inactive:
+            self._activate(sorted((mode1, mode2), reverse=True))
         self._flush([m for m in (mode1, mode2) if self._pending.get(m, ("", 0))[0] == "dense"])
         self._run_queue()  # a two-axis diagonal is not a tile operator: apply it to the current state
         tab = self._gen_diag(L.DIAG_CROSS_KERR, kappa)

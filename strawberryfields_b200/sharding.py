@@ -73,6 +73,7 @@ class ShardedCircuit(DeviceCircuit):
         self._bufs = None
         opts.pop("batch_size", None)
         opts["fuse"] = "fold"
+        opts["lazy_vacuum"] = False  # the sharded tensor always spans every mode
         super().__init__(num, trunc, pure=True, **opts)
 
     def _set_factors(self, D):
@@ -142,6 +143,7 @@ class ShardedCircuit(DeviceCircuit):
         self._phys = list(range(self._num_modes))
         self._pos = list(range(self._num_modes))
         self._untouched = set(range(self._num_modes))
+        self._inactive = set()
         self._fresh = True  # still |0..0>: the first flush may choose which modes start out sharded
 
     # ------------------------------------------------------------------ queue: everything is deferred
