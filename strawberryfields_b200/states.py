@@ -166,6 +166,27 @@ class _FockStateMixin:
             ps = np.tensordot(ps, values, axes=([1], [0]))
         return ps if self._batched else float(ps[0])
 
+    def sample_fock(self, shots, modes=None):
+        """``shots`` photon-number samples of ``modes`` (default: all) WITHOUT collapsing the state:
+        int64 array (shots, len(modes)).  The reference's ``measure_fock`` refuses ``shots != 1``
+        (fockbackend/backend.py:290-295); here the joint distribution is reduced once on the device
+        (D^k doubles come back) and numpy's global stream draws all shots from it, with the same
+        1e-8 clipping and renormalisation as a single measurement (circuit.py:678-686)."""
+        if self._batched:
+            raise NotImplementedError("sample_fock is not available for batched states")
+        modes = list(range(self._modes)) if modes is None else list(modes)
+        if len(modes) != len(set(modes)) or any(not 0 <= m < self._modes for m in modes):
+            raise ValueError("The specified modes are not valid.")
+        D, k = self._cutoff, len(modes)
+        if D ** k > 1 << 24:
+            raise NotImplementedError("sample_fock: the joint distribution of %d modes is too large" % k)
+        order = sorted(modes)
+        dist = self._view.marginal_probs_device(order).cpu().numpy().reshape(-1)
+        dist = dist * ~np.isclose(dist, 0.0)
+        idx = np.random.choice(len(dist), size=int(shots), p=dist / dist.sum())
+        digits = np.stack(np.unravel_index(idx, [D] * k), axis=1)          # columns in ascending-mode order
+        return digits[:, [order.index(m) for m in modes]].astype(np.int64)
+
     def number_expectation(self, modes):
         values = np.arange(self._cutoff)
         mean = self.diagonal_expectation(modes, values)

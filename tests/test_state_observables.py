@@ -120,6 +120,34 @@ def test_batched_observables(backend):
         assert np.abs(got["mp"][:, b] - np.array(ost.mean_photon(1))).max() < TOL
 
 
+def test_sample_fock(backend):
+    """Multi-shot sampling without collapse: outcomes follow the joint distribution, columns follow
+    the requested mode order, the state is unchanged, and one shot equals what measure_fock draws."""
+    n, D = 3, 5
+    be, ob = backend(), OracleBackend()
+    for b in (be, ob):
+        b.begin_circuit(n, cutoff_dim=D)
+        b.squeeze(0.5, 0.2, 0)
+        b.displacement(0.6, 0.1, 2)
+        b.beamsplitter(0.7, 0.3, 0, 1)
+    st = be.state()
+    probs = ob.state().all_fock_probs()
+    np.random.seed(3)
+    s = st.sample_fock(4000, modes=[2, 0])
+    assert s.shape == (4000, 2) and s.dtype == np.int64
+    marg = probs.sum(axis=1)                                # [n0, n2]
+    freq = np.zeros((D, D))
+    np.add.at(freq, (s[:, 1], s[:, 0]), 1.0 / len(s))      # column 0 is mode 2
+    assert np.abs(freq - marg).max() < 0.03
+    assert np.abs(be.state().ket() - ob.state().data).max() < TOL   # no collapse
+    np.random.seed(9)
+    one = st.sample_fock(1, modes=[1, 2])
+    np.random.seed(9)
+    assert np.array_equal(one, ob.measure_fock([1, 2]))
+    with pytest.raises(ValueError, match="not valid"):
+        st.sample_fock(2, modes=[0, 0])
+
+
 def test_argument_errors(backend):
     be = backend()
     be.begin_circuit(2, cutoff_dim=4)
