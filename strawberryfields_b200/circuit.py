@@ -793,9 +793,18 @@ class DeviceCircuit:
         modes = list(modes)
         if self._batched:
             raise NotImplementedError("state preparation on a batched b200fock circuit is not supported yet")
+        D, n, k = self._trunc, self._num_modes, len(modes)
+        if (k == 1 and modes[0] in self._inactive and not self._strict and n > 1
+                and np.shape(state) == (D,)):
+            # lazy vacuum: the mode is still a product factor, which simply becomes the new ket (stored
+            # as the pending operator whose column 0 it is); the state stays pure
+            tab = np.zeros((D, D), dtype=C128)
+            tab[:, 0] = np.asarray(state, dtype=C128)
+            self._pending[modes[0]] = ("dense", self._upload_matrix(tab))
+            self._touch(modes[0])
+            return
         self._flush()
         self._canonicalize()
-        D, n, k = self._trunc, self._num_modes, len(modes)
         pure_shape, mixed_shape = (D,) * k, (D,) * (2 * k)
         state = np.asarray(state)
         if state.shape == (D ** k,):
