@@ -212,8 +212,12 @@ class ShardedCircuit(DeviceCircuit):
         """Map both state buffers of every rank into this process (CUDA IPC through torch's storage
         sharing) and enable peer access, so that a kernel here can read a peer's shard directly.
         Collective; returns True only if it worked on every rank."""
-        if self.device.type != "cuda" or self._xmode == "nccl" or self._world == 1:
+        if self._xmode == "nccl" or self._world == 1:
             return False
+        if self.device.type != "cuda":
+            # CPU test double (gloo tests, exchange="p2p" only): the "peer memory" is POSIX shared memory,
+            # so the pull logic below -- bases, strides, ping-pong, barriers -- runs without a GPU
+            return self._xmode == "p2p" and self._setup_shared_host(size)
         ok = True
         peers = None
         # Every collective below is reached by every rank whatever fails locally (a rank that bailed
@@ -260,6 +264,26 @@ class ShardedCircuit(DeviceCircuit):
             self._peers = None
         return ok
 
+    def _setup_shared_host(self, size):
+        self._bufs = [self._new(size).share_memory_() for _ in range(2)]
+        shared = [(b.untyped_storage()._share_filename_cpu_(), b.storage_offset()) for b in self._bufs]
+        everyone = [None] * self._world
+        dist.all_gather_object(everyone, shared, group=self._pg)
+        self._peers = [[None] * self._world for _ in range(2)]
+        for r, sh in enumerate(everyone):
+            for i in range(2):
+                if r == self._rank:
+                    self._peers[i][r] = self._bufs[i]
+                    continue
+                handle, offset = sh[i]
+                st = torch.UntypedStorage._new_shared_filename_cpu(*handle)
+                self._peers[i][r] = torch.empty(0, dtype=torch.complex128).set_(st, offset, (size,), (1,))
+        return True
+
+    def _sync(self):
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
+
     def _exchange_p2p(self, T):
         """Exchange without staging: for every source rank, ONE strided-gather launch reads that
         rank's block of the old layout straight out of its HBM over NVLink and writes it where it
@@ -269,7 +293,7 @@ class ShardedCircuit(DeviceCircuit):
         ls = [self._local_stride(p) for p in range(n)]
         sub = [D // p for p in self._ps]
         prof = self.__dict__.get("profile")
-        torch.cuda.synchronize(self.device)
+        self._sync()
         dist.barrier(group=self._pg)  # every rank's current shard is final and may be read
         if prof is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -292,7 +316,7 @@ class ShardedCircuit(DeviceCircuit):
             self._gather(self._peers[self._cur][s], None, dst, oa, base=(base_a, 0, base_c))
         if prof is not None:
             ev1.record()
-        torch.cuda.synchronize(self.device)
+        self._sync()
         dist.barrier(group=self._pg)  # nobody still reads the old shards
         if prof is not None:
             nbytes = 16 * size * (self._world - 1) // self._world
