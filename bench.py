@@ -447,9 +447,13 @@ def b200_arm(args):
                     (sum(nb for nb, _ in ex) / sum(t for _, t in ex) / 1e9) if ex else None,
                 "exchanges_in_timed_region": int(exchanges),
             }
-            line["exchange"]["mode"] = ("peer-memory pull kernel (NVLink P2P loads, no staging)"
-                                        if getattr(be.circuit, "_p2p", False) else "pack + NCCL all_to_all + unpack")
-            for part in ("p2p_pull", "pack", "all_to_all", "unpack"):
+            if not getattr(be.circuit, "_p2p", False):
+                line["exchange"]["mode"] = "pack + NCCL all_to_all + unpack"
+            elif args.exchange == "push":
+                line["exchange"]["mode"] = "peer-memory push kernel (NVLink P2P stores, no staging)"
+            else:
+                line["exchange"]["mode"] = "peer-memory pull kernel (NVLink P2P loads, no staging)"
+            for part in ("p2p_pull", "p2p_push", "pack", "all_to_all", "unpack"):
                 sel = [(nb, a.elapsed_time(b) * 1e-3) for tag, nb, a, b in prof if tag == "exchange/" + part]
                 if sel:
                     line["exchange"][part] = {"ms": sum(t for _, t in sel) / len(sel) * 1e3,
@@ -473,8 +477,9 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4"],
                     help="c2 (default; c5 when sharded over N > 1 GPUs), c3 = mixed state + loss, c4 = batched QNN layer")
     ap.add_argument("--batch", type=int, default=64)
-    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
-                    help="multi-GPU axis exchange: peer-memory pull kernel or pack + NCCL all-to-all + unpack")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "push", "nccl"],
+                    help="multi-GPU axis exchange: peer-memory pull kernel (auto / p2p), peer-memory push kernel "
+                         "(experimental), or pack + NCCL all-to-all + unpack")
     ap.add_argument("--fuse", default="fold", choices=["tile", "fold", "off"],
                     help="gate queue: diagonal / same-mode folding (default), + multi-gate tile passes, "
                          "or one pass per gate")

@@ -66,9 +66,13 @@ class ShardedCircuit(DeviceCircuit):
         self.exchanges = 0
         self.exchange_bytes = 0
         # "p2p": one gather kernel per source rank reads the peers' shards straight over NVLink (no
-        # pack / unpack, no staging buffers); "nccl": pack -> all_to_all_single -> unpack; "auto": p2p
-        # when every rank can map every peer's buffers, else nccl
+        # pack / unpack, no staging buffers); "push": the same kernels with the DESTINATION remote (posted
+        # stores into the peers' new shards; host logic verified on the CPU, not yet run or timed on GPUs);
+        # "nccl": pack -> all_to_all_single -> unpack; "auto": p2p when every rank can map every peer's
+        # buffers, else nccl
         self._xmode = opts.pop("exchange", "auto")
+        if self._xmode not in ("auto", "p2p", "push", "nccl"):
+            raise ValueError("exchange must be 'auto', 'p2p', 'push' or 'nccl'")
         self._p2p = False
         self._bufs = None
         opts.pop("batch_size", None)
@@ -217,7 +221,7 @@ class ShardedCircuit(DeviceCircuit):
         if self.device.type != "cuda":
             # CPU test double (gloo tests, exchange="p2p" only): the "peer memory" is POSIX shared memory,
             # so the pull logic below -- bases, strides, ping-pong, barriers -- runs without a GPU
-            return self._xmode == "p2p" and self._setup_shared_host(size)
+            return self._xmode in ("p2p", "push") and self._setup_shared_host(size)
         ok = True
         peers = None
         # Every collective below is reached by every rank whatever fails locally (a rank that bailed
@@ -257,7 +261,7 @@ class ShardedCircuit(DeviceCircuit):
         if ok:
             self._peers = peers
         else:
-            if self._xmode == "p2p":
+            if self._xmode in ("p2p", "push"):
                 raise L.B200Error("peer-memory exchange requested but not available: %s"
                                   % getattr(self, "_p2p_error", "a peer failed"))
             self._bufs = self._bufs[:1]
@@ -293,8 +297,11 @@ class ShardedCircuit(DeviceCircuit):
         ls = [self._local_stride(p) for p in range(n)]
         sub = [D // p for p in self._ps]
         prof = self.__dict__.get("profile")
+        push = self._xmode == "push"
+        # pull: every rank's current shard is final and may be read.  push: every rank has stopped using
+        # its other ping-pong buffer (a slower rank may still be reading it in _project_reset)
         self._sync()
-        dist.barrier(group=self._pg)  # every rank's current shard is final and may be read
+        dist.barrier(group=self._pg)
         if prof is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
@@ -308,19 +315,26 @@ class ShardedCircuit(DeviceCircuit):
                 oa.append((sub[k], ls[k], 0, ls[pos]))
             else:
                 oa.append((D, ls[pos], 0, ls[pos]))
-        base_a = sum(self._digits[k] * sub[k] * ls[T[k]] for k in range(g))  # my digit selects what I pull
+        def block(digits):
+            return sum(digits[k] * sub[k] * ls[T[k]] for k in range(g))
+
         for step in range(self._world):
             s = (self._rank + step) % self._world   # start with the local block, then walk the ring
             sd = self._digits_of(s)
-            base_c = sum(sd[k] * sub[k] * ls[T[k]] for k in range(g))  # the sender's digit lands on axis T[k]
-            self._gather(self._peers[self._cur][s], None, dst, oa, base=(base_a, 0, base_c))
+            if push:
+                # posted remote stores: my block for rank s goes straight into ITS new shard
+                self._gather(self._buf, None, self._peers[1 - self._cur][s], oa,
+                             base=(block(sd), 0, block(self._digits)))
+            else:
+                # remote loads: the receiver's digit selects the block, the sender's digit lands on axis T[k]
+                self._gather(self._peers[self._cur][s], None, dst, oa, base=(block(self._digits), 0, block(sd)))
         if prof is not None:
             ev1.record()
         self._sync()
         dist.barrier(group=self._pg)  # nobody still reads the old shards
         if prof is not None:
             nbytes = 16 * size * (self._world - 1) // self._world
-            prof.append(("exchange/p2p_pull", nbytes, ev0, ev1))
+            prof.append(("exchange/p2p_push" if push else "exchange/p2p_pull", nbytes, ev0, ev1))
             prof.append(("exchange", nbytes, ev0, ev1))
         self._cur ^= 1
         self._buf = dst

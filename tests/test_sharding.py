@@ -56,14 +56,15 @@ def test_factor_world():
 
 @pytest.mark.parametrize("world,n,D,exchange", [(2, 4, 4, "auto"), (3, 4, 6, "auto"), (4, 5, 6, "auto"),
                                                 (8, 8, 2, "auto"), (2, 4, 4, "p2p"), (4, 5, 6, "p2p"),
-                                                (8, 8, 2, "p2p")])
+                                                (8, 8, 2, "p2p"), (3, 4, 6, "push"), (4, 5, 6, "push"),
+                                                (8, 8, 2, "push")])
 def test_sharded_circuit_matches_oracle_gloo(world, n, D, exchange):
     """exchange="auto" on the CPU is pack -> all_to_all_single -> unpack; "p2p" runs the peer-memory pull
     path (one strided gather per source rank, ping-pong buffers) with POSIX shared memory standing in
     for the NVLink-mapped peer buffers."""
     lines = _run("host", world, n, D, exchange)
     assert lines[0]["exchanges"] >= 1  # the circuit touches sharded modes: at least one all-to-all
-    assert all(l["p2p"] == (exchange == "p2p") for l in lines)
+    assert all(l["p2p"] == (exchange in ("p2p", "push")) for l in lines)
     if world == 8:  # three sharded axes: the planner starts the vacuum from a layout of its own choice
         assert lines[0]["free_layout"]
 
