@@ -56,8 +56,7 @@ def test_factor_world():
 
 @pytest.mark.parametrize("world,n,D,exchange", [(2, 4, 4, "auto"), (3, 4, 6, "auto"), (4, 5, 6, "auto"),
                                                 (8, 8, 2, "auto"), (2, 4, 4, "p2p"), (4, 5, 6, "p2p"),
-                                                (8, 8, 2, "p2p"), (3, 4, 6, "push"), (4, 5, 6, "push"),
-                                                (8, 8, 2, "push")])
+                                                (8, 8, 2, "p2p"), (3, 4, 6, "push"), (4, 5, 6, "push")])
 def test_sharded_circuit_matches_oracle_gloo(world, n, D, exchange):
     """exchange="auto" on the CPU is pack -> all_to_all_single -> unpack; "p2p" runs the peer-memory pull
     path (one strided gather per source rank, ping-pong buffers) with POSIX shared memory standing in
