@@ -153,8 +153,13 @@ class TorchCircuit:
     ``(batch_size,)``.  Method names and argument order follow the backend API
     (``/root/reference/strawberryfields/backends/base.py:155-621``)."""
 
-    def __init__(self, num_modes, cutoff_dim, batch_size=None, device=None):
+    def __init__(self, num_modes, cutoff_dim, batch_size=None, device=None, checkpoint_every=None,
+                 checkpoint_bytes=16 << 30):
         self.num_modes, self.cutoff, self.batch_size = int(num_modes), int(cutoff_dim), batch_size
+        # Stored states: one per differentiable gate (checkpoint_every=1), or every c-th with the ones in
+        # between recomputed during the backward pass (one more forward pass per gate, c + K/c states).
+        # None: 1 while K states fit in ``checkpoint_bytes``, else ceil(sqrt(K)).
+        self._every, self._ckpt_bytes = checkpoint_every, int(checkpoint_bytes)
         self._work = DeviceCircuit(num_modes, cutoff_dim, pure=True, batch_size=batch_size, device=device,
                                    fuse=False)
         self.device = self._work.device
@@ -212,6 +217,14 @@ class TorchCircuit:
         out = _CircuitFn.apply(self, *self._tensors)
         shape = [self.cutoff] * self.num_modes
         return out.reshape(([self._B] if self.batch_size is not None else []) + shape)
+
+    def _checkpoint_stride(self, K):
+        if self._every is not None:
+            return max(1, int(self._every))
+        state_bytes = 16 * self._B * self.cutoff ** self.num_modes
+        if K <= 1 or K * state_bytes <= self._ckpt_bytes:
+            return 1
+        return int(np.ceil(np.sqrt(K)))
 
     # values of a gate's parameters as a [2, nb] float64 device tensor
     def _values(self, slots, tensors):
@@ -304,47 +317,56 @@ class _CircuitFn(torch.autograd.Function):
         w = prog._work
         w.reset()
         buf = w._buf
-        checkpoints, values = [], []
-        live = False  # becomes True at the first gate with a differentiable parameter
-        for name, modes, slots in prog._tape:
+        tape = list(prog._tape)
+        needs = [t.requires_grad for t in tensors]
+        needed = [any(kind == "t" and needs[v] for kind, v in slots) for _, _, slots in tape]
+        first = needed.index(True) if True in needed else len(tape)  # nothing before it is kept
+        every = prog._checkpoint_stride(len(tape) - first)
+        checkpoints, values = {}, []
+        for k, (name, modes, slots) in enumerate(tape):
             p = prog._values(slots, tensors)
-            live = live or any(kind == "t" and tensors[v].requires_grad for kind, v in slots)
-            if live:
-                checkpoints.append(buf.clone())
+            if k >= first and (k - first) % every == 0:
+                checkpoints[k] = buf.clone()       # the state BEFORE gate k
             prog._apply(buf, name, modes, prog._table(name, p, prog.cutoff))
             values.append(p)
-        ctx.prog, ctx.checkpoints, ctx.values, ctx.tape = prog, checkpoints, values, list(prog._tape)
+        ctx.prog, ctx.checkpoints, ctx.values, ctx.tape = prog, checkpoints, values, tape
+        ctx.first, ctx.every, ctx.needs = first, every, needs
         ctx.meta = [(t.shape, t.dtype, t.device) for t in tensors]
-        ctx.needs = [t.requires_grad for t in tensors]
         return buf.clone().view(prog._B, -1)
 
     @staticmethod
     def backward(ctx, grad_ket):
-        prog = ctx.prog
+        prog, tape, first = ctx.prog, ctx.tape, ctx.first
         if ctx.checkpoints is None:
             raise RuntimeError("TorchCircuit: the checkpoints were consumed by a previous backward pass")
         checkpoints, ctx.checkpoints = ctx.checkpoints, None
         lam = grad_ket.resolve_conj().to(dtype=C128, device=prog.device).contiguous().clone().reshape(-1)
         grads = [None] * len(ctx.meta)
-        needed = [any(kind == "t" and ctx.needs[v] for kind, v in slots) for _, _, slots in ctx.tape]
-        first = needed.index(True) if True in needed else len(needed)
-        for k in range(len(ctx.tape) - 1, first - 1, -1):
-            (name, modes, slots), p = ctx.tape[k], ctx.values[k]
-            psi = checkpoints.pop()
-            wanted = [j for j, (kind, v) in enumerate(slots) if kind == "t" and ctx.needs[v]]
-            if wanted:
-                dtabs = prog._derivative_tables(name, p)
-                for j in wanted:
-                    t = psi.clone() if j != wanted[-1] else psi  # the checkpoint is dead after its last use
-                    prog._apply(t, name, modes, dtabs[j])
-                    g = prog._overlap_real(lam, t)                    # [B]
-                    shape, dtype, device = ctx.meta[slots[j][1]]
-                    g = g.sum() if len(shape) == 0 else g
-                    g = g.reshape(shape).to(dtype=dtype, device=device)
-                    idx = slots[j][1]
-                    grads[idx] = g if grads[idx] is None else grads[idx] + g
-            if k > first:  # nothing before the first differentiable gate needs lambda
-                prog._apply(lam, name, modes, prog._table(name, p, prog.cutoff), adjoint=True)
+        for start in reversed(range(first, len(tape), ctx.every)):
+            end = min(start + ctx.every, len(tape))
+            # states before the gates of this segment: the stored one, the others recomputed from it
+            states = [checkpoints.pop(start)]
+            for k in range(start, end - 1):
+                nxt = states[-1].clone()
+                prog._apply(nxt, tape[k][0], tape[k][1], prog._table(tape[k][0], ctx.values[k], prog.cutoff))
+                states.append(nxt)
+            for k in range(end - 1, start - 1, -1):
+                (name, modes, slots), p = tape[k], ctx.values[k]
+                psi = states.pop()
+                wanted = [j for j, (kind, v) in enumerate(slots) if kind == "t" and ctx.needs[v]]
+                if wanted:
+                    dtabs = prog._derivative_tables(name, p)
+                    for j in wanted:
+                        t = psi.clone() if j != wanted[-1] else psi  # psi is dead after its last use
+                        prog._apply(t, name, modes, dtabs[j])
+                        g = prog._overlap_real(lam, t)                    # [B]
+                        shape, dtype, device = ctx.meta[slots[j][1]]
+                        g = g.sum() if len(shape) == 0 else g
+                        g = g.reshape(shape).to(dtype=dtype, device=device)
+                        idx = slots[j][1]
+                        grads[idx] = g if grads[idx] is None else grads[idx] + g
+                if k > first:  # nothing before the first differentiable gate needs lambda
+                    prog._apply(lam, name, modes, prog._table(name, p, prog.cutoff), adjoint=True)
         return (None,) + tuple(grads)
 
 

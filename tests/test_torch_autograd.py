@@ -249,6 +249,21 @@ def test_qnn_layers_batched_weights(make):
         assert abs(w.grad[k, i, b].item() - (vals[0] - vals[1]) / (2 * h)) < 1e-7, (k, i, b)
 
 
+@pytest.mark.parametrize("every", [2, 4, 100, None])
+def test_checkpoint_thinning_gives_the_same_gradients(every, make):
+    """Keeping every c-th state and recomputing the rest must not change a single gradient."""
+    n, D = 3, 4
+    rng = np.random.RandomState(8)
+    th0 = rng.uniform(0.05, 0.4, 15)
+    grads = []
+    for ev, budget in ((1, 16 << 30), (every, 1 if every is None else 16 << 30)):  # None + tiny budget: sqrt(K)
+        th = [torch.tensor(v, dtype=torch.float64, requires_grad=True) for v in th0]
+        prog = build(make(n, D, checkpoint_every=ev, checkpoint_bytes=budget), th)
+        loss_of(prog.ket()).backward()
+        grads.append(np.array([t.grad.item() for t in th]))
+    assert np.abs(grads[0] - grads[1]).max() < 1e-13
+
+
 def test_constant_prefix_and_second_backward(make):
     """Gates before the first differentiable one keep no checkpoint; a second backward pass over the
     same graph is refused (the checkpoints are consumed)."""
