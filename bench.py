@@ -285,7 +285,7 @@ def b200_arm(args):
     # lazy-vacuum option (modes stay product factors until a two-mode gate needs them).
     # Default: the gates are applied to whatever state the previous step left (a generic dense state),
     # i.e. the steady-state cost of the kernels alone.
-    if args.from_vacuum and not sharded and args.workload != "c3":
+    if args.from_vacuum and not sharded:
         shard_kw = dict(shard_kw, lazy_vacuum=True)
 
     def one_step(b):

@@ -241,10 +241,10 @@ class DeviceCircuit:
         self._pending = {}
         self._opq = []
         self._untouched = set(range(self._num_modes))
-        if self._lazy_opt and self._pure and self._fuse == "fold" and self._num_modes > 0:
+        if self._lazy_opt and self._fuse == "fold" and self._num_modes > 0:
             # nothing is entangled yet: the device tensor has no axes (one amplitude, 1, per batch entry)
             self._phys = []
-            self._pos = [None] * self._num_modes
+            self._pos = [None] * self._axes()
             self._inactive = set(range(self._num_modes))
             self._buf = torch.ones(self._B, dtype=torch.complex128, device=self.device)
             return
@@ -532,7 +532,8 @@ class DeviceCircuit:
         """Lazy vacuum: bring the still-factored modes among ``modes`` into the device tensor.  Such
         a mode is |0> with (at most) one pending single-mode operator P, i.e. the factor P|0> = column
         0 of P; the tensor grows by one (outermost) axis with one outer-product launch that WRITES the
-        new tensor once -- instead of a read + write pass over the full-size state per such gate."""
+        new tensor once -- instead of a read + write pass over the full-size state per such gate.
+        Mixed states: the factor is the rank-one matrix P|0><0|P^dagger on the (ket, bra) axes."""
         D, B = self._trunc, self._B
         for m in modes:
             if m not in self._inactive:
@@ -544,14 +545,22 @@ class DeviceCircuit:
                 v[:, 0] = 1.0 if pend is None else pend[1][:, 0]
             else:
                 v = pend[1][:, :, 0].contiguous()
+            nb = v.shape[0]
             old_per = self._size()
-            out = self._new(B * old_per * D)
-            oa = [(B, old_per, D if v.shape[0] > 1 else 0, old_per * D)] if B > 1 else []
-            oa += [(D, 0, 1, old_per), (old_per, 1, 0, 1)]
-            self._gather(self._buf, v, out, oa)
+            if self._pure:
+                f, new_per = v, old_per * D
+                oa = [(D, 0, 1, old_per)]
+            else:
+                # conj_physical: the kernel reads raw memory, torch's lazy conjugate bit would be lost
+                f = (v.reshape(nb, D, 1) * torch.conj_physical(v).reshape(nb, 1, D)).contiguous()
+                new_per = old_per * D * D
+                oa = [(D, 0, D, D * old_per), (D, 0, 1, old_per)]
+            out = self._new(B * new_per)
+            lead = [(B, old_per, f[0].numel() if nb > 1 else 0, new_per)] if B > 1 else []
+            self._gather(self._buf, f, out, lead + oa + [(old_per, 1, 0, 1)])
             self._buf, self._shared, self._scratch = out, False, None
             self._inactive.discard(m)
-            self._phys = [m] + self._phys
+            self._phys = list(self._mode_axes(m)) + self._phys
             for p, ax in enumerate(self._phys):
                 self._pos[ax] = p
 
@@ -794,7 +803,7 @@ class DeviceCircuit:
         if self._batched:
             raise NotImplementedError("state preparation on a batched b200fock circuit is not supported yet")
         D, n, k = self._trunc, self._num_modes, len(modes)
-        if (k == 1 and modes[0] in self._inactive and not self._strict and n > 1
+        if (k == 1 and modes[0] in self._inactive and (not self._strict or not self._pure) and n > 1
                 and np.shape(state) == (D,)):
             # lazy vacuum: the mode is still a product factor, which simply becomes the new ket (stored
             # as the pending operator whose column 0 it is); the state stays pure
@@ -890,7 +899,7 @@ class DeviceCircuit:
         self.prepare_multimode(state, [mode] if isinstance(mode, int) else mode)
 
     def _prepare_ket(self, ket, mode):
-        if self._pure:
+        if self._pure or (mode in self._inactive and self._num_modes > 1):  # lazy vacuum: the factor is the ket
             self.prepare(ket, mode)
         else:
             self.prepare(np.outer(ket, ket.conj()), mode)

@@ -16,6 +16,8 @@ single)
       > gpurun_out/r02_bench_c2_from_vacuum.json 2> gpurun_out/r02_bench_c2_from_vacuum.err
   timeout 300 python bench.py --steps 10 --warmup 3 --workload c4 --from-vacuum --no-cpu-baseline \
       > gpurun_out/r02_bench_c4_from_vacuum.json 2>&1
+  timeout 300 python bench.py --steps 10 --warmup 3 --workload c3 --from-vacuum --no-cpu-baseline \
+      > gpurun_out/r02_bench_c3_from_vacuum.json 2>&1
   # 3. the differentiable path: one QNN training run
   timeout 300 python examples/qnn_torch.py --modes 2 --layers 4 --cutoff 10 --steps 40 > gpurun_out/r02_qnn_torch.log 2>&1
   ;;
