@@ -44,6 +44,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "fock_amp_gate_updates_per_s"
 UNIT = "updates/s"
+DEVICE = "cuda"  # where the timing scalars and the e2e parameter table live (the CPU dry-run test overrides it)
 
 
 # ------------------------------------------------------------------------------ helpers
@@ -245,7 +246,10 @@ def b200_arm(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        if DEVICE == "cuda":
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        else:  # CPU dry-run of the control flow (tests/test_bench_dryrun.py)
+            dist.init_process_group("gloo")
     handle = lib.load(build_if_missing=False)
 
     # N = 1: BASELINE config 2 (8 modes).  N > 1: BASELINE config 5 -- ONE 9-mode state sharded over
@@ -310,7 +314,7 @@ def b200_arm(args):
     barrier()
     launches = int(handle.b200_launch_count())
     clocks = sampler.stop()
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=DEVICE)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
@@ -380,7 +384,7 @@ def b200_arm(args):
     be2.begin_circuit(n_modes, cutoff_dim=D, fuse=fuse, **shard_kw)
 
     def e2e_step():
-        dev_params = pinned.to("cuda", non_blocking=True)  # H2D of the step's inputs
+        dev_params = pinned.to(DEVICE, non_blocking=True)  # H2D of the step's inputs
         be2.reset(pure=args.workload != "c3")  # what LocalEngine.reset() does between runs (engine.py:413-417)
         for i, c in enumerate(calls):
             modes = [x for x in c[1:] if isinstance(x, (int, np.integer))]
@@ -398,7 +402,7 @@ def b200_arm(args):
     e1.record()
     barrier()
     wall = time.perf_counter() - t0
-    ms2 = torch.tensor([max(e0.elapsed_time(e1), wall * 1e3)], dtype=torch.float64, device="cuda")
+    ms2 = torch.tensor([max(e0.elapsed_time(e1), wall * 1e3)], dtype=torch.float64, device=DEVICE)
     if world > 1:
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e_value = updates_per_step * args.steps / (float(ms2.item()) * 1e-3)
@@ -424,8 +428,8 @@ def b200_arm(args):
             "config": {
                 "workload": "BASELINE config %s; cutoff %d, %.3g stored complex128 elements, %d gates per step"
                             % (wl_name, D, elements, len(calls)),
-                "parallelism": ("state sharded on its leading axes over %d ranks, NCCL all-to-all axis exchange"
-                                % world) if sharded else "single GPU",
+                "parallelism": ("state sharded on its leading axes over %d ranks, all-to-all axis exchange over "
+                                "NVLink (see exchange.mode)" % world) if sharded else "single GPU",
                 "l2": "state %.2f GB per GPU > 126 MB L2: every pass streams from HBM"
                       % (local_elements * 16 / 1e9),
                 "passes_per_step": sum(v[2] for v in by_tag.values()),
