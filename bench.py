@@ -289,7 +289,7 @@ def b200_arm(args):
     # lazy-vacuum option (modes stay product factors until a two-mode gate needs them).
     # Default: the gates are applied to whatever state the previous step left (a generic dense state),
     # i.e. the steady-state cost of the kernels alone.
-    if args.from_vacuum and not sharded:
+    if args.from_vacuum:
         shard_kw = dict(shard_kw, lazy_vacuum=True)
 
     def one_step(b):

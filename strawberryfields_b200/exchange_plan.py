@@ -147,6 +147,28 @@ def search(op_axes, phys, g, left, penalty=INNER_PENALTY, bound=None):
     return None if best[1] is None else (best[0], best[1])
 
 
+def replicated_prefix(op_axes, k_max):
+    """Lazy vacuum on a sharded state: split a fresh program into the gates that can run while at
+    most ``k_max`` modes are entangled (a tensor small enough to be replicated on every rank) and
+    the rest.  Only two-mode gates entangle; single-mode gates on untouched modes just update a
+    product factor.  A gate goes to the rest when it would exceed ``k_max`` or shares a mode with a
+    gate already there (program order per mode).  Returns (replicated, rest) index lists."""
+    active, blocked, rep, rest = set(), set(), [], []
+    for i, ax in enumerate(op_axes):
+        if not blocked.isdisjoint(ax):
+            blocked.update(ax)
+            rest.append(i)
+            continue
+        grown = active | set(ax) if len(ax) > 1 else active
+        if len(grown) <= k_max:
+            active = grown
+            rep.append(i)
+        else:
+            blocked.update(ax)
+            rest.append(i)
+    return rep, rest
+
+
 def exchanges(steps):
     return sum(1 for s in steps if s[0] == "exchange")
 

@@ -77,7 +77,10 @@ class ShardedCircuit(DeviceCircuit):
         self._bufs = None
         opts.pop("batch_size", None)
         opts["fuse"] = "fold"
-        opts["lazy_vacuum"] = False  # the sharded tensor always spans every mode
+        # lazy vacuum, sharded flavour: the part of a fresh program that fits one GPU runs REPLICATED on
+        # every rank as a small lazy-vacuum circuit (no communication); see _build_from_replicated
+        self._lazy_shard = bool(opts.get("lazy_vacuum", False))
+        opts["lazy_vacuum"] = False  # the sharded tensor itself always spans every mode
         super().__init__(num, trunc, pure=True, **opts)
 
     def _set_factors(self, D):
@@ -185,6 +188,14 @@ class ShardedCircuit(DeviceCircuit):
         # derives the same one.  It never evicts the innermost axis if that can be avoided: swapping it
         # would cut the exchange into 16*D/p-byte (80 B) runs -- measured 110 GB/s instead of 590 GB/s
         # over NVLink -- and while the state is still |0..0> it may also pick the layout.
+        replicated = []
+        if self._fresh and self._lazy_shard:
+            # lazy vacuum: gates that act while at most k_max modes are entangled run replicated
+            k_max = self._num_modes
+            while self._trunc ** k_max * self._world > self._trunc ** self._num_modes:
+                k_max -= 1
+            replicated, rest = X.replicated_prefix([op.axes for op in ops], k_max)
+            all_ops, ops = ops, [ops[i] for i in rest]
         key = (tuple(op.axes for op in ops), tuple(self._phys), self._g, self._fresh)
         if key not in _PLANS:
             if len(_PLANS) >= 64:
@@ -196,6 +207,8 @@ class ShardedCircuit(DeviceCircuit):
         phys0, steps = _PLANS[key]
         if phys0 != self._phys:
             self._set_layout(phys0)
+        if replicated:
+            self._build_from_replicated([all_ops[i] for i in replicated])
         self._fresh = False
         for step in steps:
             if step[0] == "run":
@@ -203,6 +216,64 @@ class ShardedCircuit(DeviceCircuit):
                     self._exec(ops[i])
             else:
                 self._exchange(sorted(self._pos[m] for m in step[1]))
+
+    def _build_from_replicated(self, ops):
+        """Lazy vacuum on a sharded state.  ``ops`` (a dependency-closed prefix of a fresh program that
+        never entangles more modes than fit one GPU) runs on every rank as a small lazy-vacuum
+        ``DeviceCircuit`` -- redundantly, but on D^2 .. D^k_max tensors and without any exchange.  Then
+        this rank's shard is written once: its slice of the small tensor, times the factors of the modes
+        that are still untouched, straight into the layout the exchange planner chose for the rest."""
+        n, D, g = self._num_modes, self._trunc, self._g
+        rep = DeviceCircuit(n, D, pure=True, device=self.device, fuse="fold", lazy_vacuum=True)
+        if self.__dict__.get("profile") is not None:
+            rep.profile = self.profile
+        for op in ops:
+            if op.kind == S.KIND_SINGLE:
+                rep._queue_dense(op.table, op.axes[0])
+            elif op.kind == S.KIND_DIAG:
+                rep._queue_diag(op.table, op.axes[0])
+            else:
+                rep._pair_gate(op.table, op.kind, op.axes[0], op.axes[1])
+        active = list(rep._phys)
+        rep._flush(active)  # pending operators of entangled modes; factored modes keep theirs as factors
+
+        def extent(m):
+            return self._ext(self._pos[m])
+
+        def offset(m):  # first index of this rank's range on mode m
+            pos = self._pos[m]
+            return self._digits[pos] * (D // self._ps[pos]) if pos < g else 0
+
+        def contiguous(modes):
+            st, acc = {}, 1
+            for m in reversed(modes):
+                st[m] = acc
+                acc *= extent(m)
+            return st, acc
+
+        inactive = [m for m in self._phys if m not in active]
+        cur_modes = [m for m in self._phys if m in active]      # the shard's axis order
+        cur, cs = rep._buf, {}
+        if cur_modes:
+            cs, size = contiguous(cur_modes)
+            cur = self._buf if not inactive else self._new(size)
+            oa = [(extent(m), rep._stride(m), 0, cs[m]) for m in cur_modes]
+            self._gather(rep._buf, None, cur, oa, base=(sum(offset(m) * rep._stride(m) for m in cur_modes), 0, 0))
+        for t, m in enumerate(inactive):
+            pend = rep._pending.get(m)
+            v = torch.zeros(D, dtype=torch.complex128, device=self.device)
+            if pend is None:
+                v[0] = 1.0
+            elif pend[0] == "diag":
+                v[0] = pend[1][0, 0]
+            else:
+                v = pend[1][0, :, 0].contiguous()
+            new_modes = [x for x in self._phys if x == m or x in cur_modes]
+            ns, size = contiguous(new_modes)
+            out = self._buf if t == len(inactive) - 1 else self._new(size)
+            oa = [(extent(x), 0, 1, ns[x]) if x == m else (extent(x), cs[x], 0, ns[x]) for x in new_modes]
+            self._gather(cur, v, out, oa, base=(0, offset(m), 0))
+            cur, cur_modes, cs = out, new_modes, ns
 
     def _set_layout(self, phys):
         self._phys = list(phys)

@@ -42,7 +42,8 @@ def main():
              ("beamsplitter", 0.7, 0.2, 1, 0)]
     be = B200FockBackend()
     exchange = sys.argv[4] if len(sys.argv) > 4 else "auto"
-    be.begin_circuit(n, cutoff_dim=D, shard=True, exchange=exchange)
+    lazy = len(sys.argv) > 5 and sys.argv[5] == "lazy"
+    be.begin_circuit(n, cutoff_dim=D, shard=True, exchange=exchange, lazy_vacuum=lazy)
     W.run_calls(be, calls + extra)
     st = be.state()
     from strawberryfields_b200 import sharding

@@ -81,6 +81,26 @@ def test_random_queues(seed):
             assert phys0 == phys
 
 
+@pytest.mark.parametrize("n,k_max,want_rep,max_exchanges", [(9, 8, 25, 1), (10, 9, 26, 1), (8, 5, 12, 3)])
+def test_replicated_prefix(n, k_max, want_rep, max_exchanges):
+    """Lazy vacuum on sharded states: the prefix never entangles more than k_max modes, keeps the
+    program order per mode, and together with the rest covers every gate once."""
+    ops = queue_axes(n)
+    rep, rest = X.replicated_prefix(ops, k_max)
+    assert sorted(rep + rest) == list(range(len(ops))) and len(rep) == want_rep
+    entangled = set()
+    for i in rep:
+        if len(ops[i]) > 1:
+            entangled.update(ops[i])
+    assert len(entangled) <= k_max
+    for i in rep:  # nothing in the prefix comes after a postponed gate on the same mode
+        assert not any(j < i and set(ops[j]) & set(ops[i]) for j in rest)
+    # the rest is an ordinary queue for the exchange planner
+    phys0, steps = X.plan([ops[i] for i in rest], list(range(n)), 3, free_layout=True)
+    X.check([ops[i] for i in rest], phys0, 3, steps)
+    assert X.exchanges(steps) <= max_exchanges  # 9 / 10 modes on 8 ranks: ONE exchange after the prefix
+
+
 def test_no_sharding_and_empty_queue():
     assert X.plan([], [0, 1, 2], 1) == ([0, 1, 2], [])
     phys0, steps = X.plan([(0, 1), (1, 2)], [0, 1, 2], 0)

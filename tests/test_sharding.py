@@ -21,10 +21,10 @@ def _free_port():
     return port
 
 
-def _run(mode, world, n, D, exchange="auto", timeout=600):
+def _run(mode, world, n, D, exchange="auto", timeout=600, lazy=False):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
-           os.path.join(ROOT, "tests", "dist_worker.py"), mode, str(n), str(D), exchange]
+           os.path.join(ROOT, "tests", "dist_worker.py"), mode, str(n), str(D), exchange] + (["lazy"] if lazy else [])
     # start_new_session: on a timeout the whole torchrun process group is killed, nothing is left behind
     proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, start_new_session=True)
     try:
@@ -55,8 +55,8 @@ def test_factor_world():
 
 
 @pytest.mark.parametrize("world,n,D,exchange", [(2, 4, 4, "auto"), (3, 4, 6, "auto"), (4, 5, 6, "auto"),
-                                                (8, 8, 2, "auto"), (2, 4, 4, "p2p"), (4, 5, 6, "p2p"),
-                                                (8, 8, 2, "p2p"), (3, 4, 6, "push"), (4, 5, 6, "push")])
+                                                (8, 8, 2, "auto"), (4, 5, 6, "p2p"), (8, 8, 2, "p2p"),
+                                                (4, 5, 6, "push")])
 def test_sharded_circuit_matches_oracle_gloo(world, n, D, exchange):
     """exchange="auto" on the CPU is pack -> all_to_all_single -> unpack; "p2p" runs the peer-memory pull
     path (one strided gather per source rank, ping-pong buffers) with POSIX shared memory standing in
@@ -66,6 +66,15 @@ def test_sharded_circuit_matches_oracle_gloo(world, n, D, exchange):
     assert all(l["p2p"] == (exchange in ("p2p", "push")) for l in lines)
     if world == 8:  # three sharded axes: the planner starts the vacuum from a layout of its own choice
         assert lines[0]["free_layout"]
+
+
+@pytest.mark.parametrize("world,n,D,exchange", [(4, 5, 6, "p2p"), (8, 8, 2, "auto")])
+def test_sharded_lazy_vacuum_matches_oracle_gloo(world, n, D, exchange):
+    """lazy_vacuum=True on a sharded circuit: the prefix of the program that fits one rank runs replicated
+    as a small lazy-vacuum circuit, then every rank writes its shard once; same ket, same
+    measurement outcome (asserted by the worker on every rank)."""
+    lines = _run("host", world, n, D, exchange, lazy=True)
+    assert all(l["p2p"] == (exchange == "p2p") for l in lines)
 
 
 @pytest.mark.gpu

@@ -29,6 +29,12 @@ multi)
           > gpurun_out/r02_bench_n${n}_${ex}.json 2> gpurun_out/r02_bench_n${n}_${ex}.err
     done
   done
+  # whole program runs from vacuum with the sharded lazy vacuum (replicated prefix, one exchange)
+  for m in 9 10; do
+    timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
+        --master-port 29520 bench.py --gpus 8 --modes $m --steps 3 --warmup 3 --from-vacuum --no-cpu-baseline \
+        > gpurun_out/r02_bench_n8_${m}modes_from_vacuum.json 2> gpurun_out/r02_bench_n8_${m}modes_from_vacuum.err
+  done
   timeout 200 python -m pytest tests/test_sharding.py -q -m gpu 2>&1 | tail -5 > gpurun_out/r02_pytest_sharding_gpu.log
   ;;
 esac
