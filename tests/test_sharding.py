@@ -91,3 +91,16 @@ def test_sharded_circuit_matches_oracle_on_gpus(exchange):
     # but the round's GPU budget ended before a 4-GPU re-run.  bench.py at 4 / 8 ranks was not affected.
     lines = _run("gpu", 2, 5, 6, exchange, timeout=150)
     assert all(l["p2p"] == (exchange == "p2p") for l in lines)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("exchange,lazy", [("push", False), ("p2p", True)])
+def test_sharded_paths_written_after_round1_on_gpus(exchange, lazy):
+    """The push form of the peer-memory exchange and the sharded lazy vacuum: host logic verified on the CPU
+    doubles above, first GPU run pending (round 1's GPU budget ended before they were written)."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    lines = _run("gpu", 2, 5, 6, exchange, timeout=150, lazy=lazy)
+    assert all(l["p2p"] for l in lines)
