@@ -20,6 +20,7 @@ single)
       > gpurun_out/r02_bench_c3_from_vacuum.json 2>&1
   # 3. the differentiable path: one QNN training run
   timeout 300 python examples/qnn_torch.py --modes 2 --layers 4 --cutoff 10 --steps 40 > gpurun_out/r02_qnn_torch.log 2>&1
+  timeout 300 python tools/bench_autodiff.py > gpurun_out/r02_bench_autodiff_c4.json 2> gpurun_out/r02_bench_autodiff_c4.err
   ;;
 multi)
   for n in 2 4 8; do
