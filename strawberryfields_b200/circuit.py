@@ -325,8 +325,20 @@ class DeviceCircuit:
         e1.record()
         prof.append((tag, 32 * self._B * self._size(), e0, e1))
 
+    def _check_launch(self, table, per_entry, *strides):
+        """Host-side bounds of a gate launch: the buffer holds B states of _size() elements, every gate
+        axis lies inside one state, the table holds one entry (or B) of ``per_entry`` coefficients."""
+        size, D = self._size(), self._trunc
+        if self._buf.numel() < self._B * size:
+            raise L.B200Error("state buffer holds %d elements, the launch covers %d" % (self._buf.numel(), self._B * size))
+        if any(s < 1 or s * D > size for s in strides):
+            raise L.B200Error("gate axis stride %r does not fit a state of %d elements" % (strides, size))
+        if table.shape[0] not in (1, self._B) or table.numel() < table.shape[0] * per_entry:
+            raise L.B200Error("gate table of shape %r for a batch of %d" % (tuple(table.shape), self._B))
+
     def _k_gate1(self, U, axis, conj):
         self._own()
+        self._check_launch(U, self._trunc ** 2, self._stride(axis))
         D, B = self._trunc, self._B
         naxes = len(self._phys)
         nb = U.shape[0]
@@ -338,6 +350,7 @@ class DeviceCircuit:
 
     def _k_gate2(self, G, rule, ax1, ax2, conj):
         self._own()
+        self._check_launch(G, L.packed_size(self._trunc), self._stride(ax1), self._stride(ax2))
         D, B = self._trunc, self._B
         nb = G.shape[0]
         naxes = len(self._phys)
@@ -351,6 +364,7 @@ class DeviceCircuit:
 
     def _k_diag_pair(self, tab, ax1, ax2, conj):
         self._own()
+        self._check_launch(tab, self._trunc ** 2, self._stride(ax1), self._stride(ax2))
         D, B = self._trunc, self._B
         nb = tab.shape[0]
         self._pass("diag2", "b200_apply_diag", _ptr(self._buf), self._size(), D, self._stride(ax1), self._stride(ax2),
@@ -367,6 +381,8 @@ class DeviceCircuit:
             else:
                 axes.append((self._stride(2 * mode), 0, tab))
                 axes.append((self._stride(2 * mode + 1), 1, tab))
+        for s, _, tab in axes:
+            self._check_launch(tab, D, s)
         for i in range(0, len(axes), L.MAX_AXES):
             chunk = axes[i:i + L.MAX_AXES]
             nb = max(t.shape[0] for _, _, t in chunk)
@@ -689,6 +705,17 @@ class DeviceCircuit:
         oa, ra = merge(list(out_axes), 4), merge(list(red_axes), 3)
         if len(oa) > L.MAX_AXES or len(ra) > L.MAX_AXES:
             raise L.B200Error("tensor rank exceeds the gather kernel's limit")
+        # every index the launch can form must lie inside its tensor: a wrong stride fails here, loudly,
+        # instead of as an illegal address on the device (and is caught by the CPU suite too)
+        for name, t, b0, col, rcol in (("A", A, base[0], 1, 1), ("B", B, base[1], 2, 2), ("C", Cout, base[2], 3, None)):
+            if t is None:
+                continue
+            pairs = [(a[0], a[col]) for a in oa] + ([(r[0], r[rcol]) for r in ra] if rcol is not None else [])
+            lo = b0 + sum((e - 1) * s for e, s in pairs if s < 0)
+            hi = b0 + sum((e - 1) * s for e, s in pairs if s > 0)
+            if lo < 0 or hi >= t.numel():
+                raise L.B200Error("gather descriptor addresses [%d, %d] of operand %s with %d elements"
+                                  % (lo, hi, name, t.numel()))
         d = L.GatherDesc()
         d.n_out_axes, d.n_red_axes = len(oa), len(ra)
         for j, (e, sa, sb, sc) in enumerate(oa):
