@@ -164,3 +164,26 @@ def test_config2_full_size_passes_drop(backend, monkeypatch):
         kets.append(len(full))
     assert np.abs(kets[0] - kets[2]).max() < TOL
     assert kets[1] <= kets[3] - n  # at least the n single-mode passes are gone
+
+
+@pytest.mark.gpu
+def test_full_size_config2_lazy_equals_eager_on_gpu():
+    """BASELINE config 2 at full size (8 modes, cutoff 10, 1e8 amplitudes) from vacuum: the lazy-vacuum
+    run and the eager run give the same state (norm, a list of amplitudes, single-mode marginals)."""
+    from strawberryfields_b200 import workloads as W
+    from strawberryfields_b200.backend import B200FockBackend
+
+    n, D = 8, 10
+    calls = W.config2_circuit(n, seed=42)
+    idx = [[0] * n, [1] + [0] * (n - 1), [0, 1, 0, 2, 0, 0, 1, 0], [0] * (n - 1) + [3], [1] * n]
+    res = []
+    for lazy in (False, True):
+        be = B200FockBackend()
+        be.begin_circuit(n, cutoff_dim=D, lazy_vacuum=lazy)
+        W.run_calls(be, calls)
+        st = be.state()
+        res.append((st.trace(), np.array([be.circuit.element(i)[0] for i in idx]),
+                    np.stack([np.stack(st.mean_photon(m)) for m in range(n)])))
+    assert abs(res[0][0] - res[1][0]) < TOL
+    assert np.abs(res[0][1] - res[1][1]).max() < TOL
+    assert np.abs(res[0][2] - res[1][2]).max() < 1e-11
