@@ -152,10 +152,10 @@ class B200FockBackend(_Base):
             # pure state sharded over the ranks of the (default or given) torch.distributed group
             from .sharding import ShardedCircuit
 
-            if not pure or batch_size is not None:
-                raise NotImplementedError("sharded b200fock circuits hold unbatched pure states only")
+            if batch_size is not None:
+                raise NotImplementedError("sharded b200fock circuits are not batched (shard the batch instead)")
             group = None if shard is True else shard
-            self.circuit = ShardedCircuit(num_subsystems, cutoff_dim, group=group,
+            self.circuit = ShardedCircuit(num_subsystems, cutoff_dim, group=group, pure=pure,
                                           exchange=kwargs.get("exchange", "auto"), **self._options)
         else:
             self.circuit = DeviceCircuit(num_subsystems, cutoff_dim, pure, batch_size=batch_size, **self._options)

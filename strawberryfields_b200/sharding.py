@@ -1,8 +1,11 @@
-"""Pure states sharded over several GPUs (one process per GPU, ``torch.distributed``).
+"""States sharded over several GPUs (one process per GPU, ``torch.distributed``).
 
 The reference has no distributed path; this is the scale-out row of
-the hot-path scope table (section 8e): a D^n state that does not fit, or should not sit,
-on one GPU is cut along its LEADING tensor axes.
+the hot-path scope table (section 8e): a D^n ket -- or a D^2n density matrix with its
+(ket_0, bra_0, ket_1, ..) axes -- that does not fit, or should not sit, on one GPU is cut
+along its LEADING tensor axes.  Everything below speaks of tensor axes; for a ket axis m is
+mode m, for a density matrix a gate is one queue entry on the ket axes and one (conjugated)
+on the bra axes, and reductions walk the ket = bra diagonal across the ranks (``_walk``).
 
 Layout.  The world size P is factored as p_0 * p_1 * ... * p_{g-1} with every p_k a divisor
 of the cutoff D (D = 10: P = 2, 4, 8 -> (2), (2,2), (2,2,2)).  Physical axis k < g is split
@@ -61,7 +64,8 @@ class ShardedCircuit(DeviceCircuit):
         self._rank = dist.get_rank(group)
         self._world = dist.get_world_size(group)
         self._set_factors(trunc)
-        if self._g > num - 1:
+        pure = opts.pop("pure", True)
+        if self._g > (num if pure else 2 * num) - 1:
             raise ValueError("%d modes are too few to shard over %d ranks at cutoff %d" % (num, self._world, trunc))
         self.exchanges = 0
         self.exchange_bytes = 0
@@ -81,7 +85,7 @@ class ShardedCircuit(DeviceCircuit):
         # every rank as a small lazy-vacuum circuit (no communication); see _build_from_replicated
         self._lazy_shard = bool(opts.get("lazy_vacuum", False))
         opts["lazy_vacuum"] = False  # the sharded tensor itself always spans every mode
-        super().__init__(num, trunc, pure=True, **opts)
+        super().__init__(num, trunc, pure=pure, **opts)
 
     def _set_factors(self, D):
         self._ps = factor_world(self._world, D)
@@ -101,54 +105,119 @@ class ShardedCircuit(DeviceCircuit):
 
     def _size(self):
         n = 1
-        for pos in range(self._num_modes):
+        for pos in range(self._axes()):
             n *= self._ext(pos)
         return n
 
     def _local_stride(self, pos):
         s = 1
-        for q in range(pos + 1, self._num_modes):
+        for q in range(pos + 1, self._axes()):
             s *= self._ext(q)
         return s
 
     def _stride(self, axis):
         return self._local_stride(self._pos[axis])
 
+    def _range(self, axis):
+        """global index range [lo, hi) of tensor axis ``axis`` held by this rank"""
+        pos = self._pos[axis]
+        if pos >= self._g:
+            return 0, self._trunc
+        sub = self._trunc // self._ps[pos]
+        return self._digits[pos] * sub, (self._digits[pos] + 1) * sub
+
     def _canonicalize(self):  # the sharded layout is never canonical; readers go through _stride()
         return
 
-    def _to_mixed(self):
-        raise NotImplementedError("mixed states are not sharded yet (loss / del_mode / measurement on a "
-                                  "sharded b200fock circuit)")
-
-    def reset(self, pure=None, cutoff_dim=None, num_subsystems=None):
-        if pure is False:
-            raise NotImplementedError("sharded b200fock circuits hold pure states only")
-        if num_subsystems is not None:
-            self._num_modes = num_subsystems
-        if cutoff_dim is not None:
-            if cutoff_dim != getattr(self, "_trunc", cutoff_dim):
-                self._set_factors(cutoff_dim)
-            self._trunc = cutoff_dim
-        self._pure = True
-        self._scratch = self._send = self._recv = None
-        self._shared = False
+    def _alloc(self):
+        """(Re)allocate the two ping-pong state buffers for the current geometry and map them into the
+        peers when possible.  Collective."""
         size = self._size()
         if self._bufs is None or self._bufs[0].numel() != size:
-            # two state buffers (ping-pong target of the exchange), mapped into every peer when possible
             self._bufs = None
             self._buf = None
             self._bufs = [self._new(size)]
             self._p2p = self._setup_p2p(size)
         self._cur = 0
         self._buf = self._bufs[0]
+        self._scratch = self._send = self._recv = None
+        self._shared = False
+
+    def _to_mixed(self):
+        """psi -> |psi><psi| with interleaved (ket, bra) axes (ops.py:110-120), sharded on the leading
+        axes of the new 2n-axis tensor.  The ket is small next to the density matrix (D^n against
+        D^2n / P per rank), so every rank gathers all of it and writes its own shard of the outer
+        product; no exchange of the big tensor is needed."""
+        if not self._pure:
+            return
+        self._flush()
+        n, D = self._num_modes, self._trunc
+        parts = [torch.empty_like(self._buf) for _ in range(self._world)]
+        dist.all_gather(parts, self._buf, group=self._pg)
+        full = torch.stack(parts).reshape(-1)          # [rank digits][local layout]
+        # strides of mode m inside ``full``: position pos of the OLD layout; sharded axes split in (digit, rest)
+        old_ls = [self._local_stride(p) for p in range(n)]
+        old_pos, old_size = list(self._pos), self._size()
+        rank_stride = []                               # stride of digit k in ``full``
+        acc = old_size
+        for p in reversed(self._ps):
+            rank_stride.append(acc)
+            acc *= p
+        rank_stride.reverse()
+
+        def psi_axes(m, lo, hi):
+            """(ext, stride) pairs + base offset that walk psi along mode m over the global range [lo, hi)"""
+            pos = old_pos[m]
+            if pos >= self._g:
+                return [(hi - lo, old_ls[pos])], lo * old_ls[pos]
+            sub = D // self._ps[pos]
+            if lo % sub == 0 and (hi - lo) % sub == 0:  # whole old digits: digit-major, then the remainder
+                return [((hi - lo) // sub, rank_stride[pos]), (sub, old_ls[pos])], (lo // sub) * rank_stride[pos]
+            if lo // sub == (hi - 1) // sub:            # inside one old digit
+                return [(hi - lo, old_ls[pos])], (lo // sub) * rank_stride[pos] + (lo % sub) * old_ls[pos]
+            raise NotImplementedError("pure -> mixed on a sharded state with these rank factors %r" % (self._ps,))
+
+        self._pure = False
+        self._phys = list(range(2 * n))
+        self._pos = list(range(2 * n))
+        self._bufs = None
+        self._alloc()
+        oa, base_a, base_b = [], 0, 0
+        for ax in range(2 * n):
+            lo, hi = self._range(ax)
+            pairs, off = psi_axes(ax // 2, lo, hi)
+            st = self._stride(ax)
+            ext_left = hi - lo
+            for e, s in pairs:                         # outer pair first: its output stride spans the inner one
+                ext_left //= e
+                if ax % 2 == 0:
+                    oa.append((e, s, 0, st * ext_left))
+                else:
+                    oa.append((e, 0, s, st * ext_left))
+            if ax % 2 == 0:
+                base_a += off
+            else:
+                base_b += off
+        self._gather(full, full, self._buf, oa, flags=L.FLAG_CONJ_B, base=(base_a, base_b, 0))
+        self._fresh = False
+
+    def reset(self, pure=None, cutoff_dim=None, num_subsystems=None):
+        if num_subsystems is not None:
+            self._num_modes = num_subsystems
+        if cutoff_dim is not None:
+            if cutoff_dim != getattr(self, "_trunc", cutoff_dim):
+                self._set_factors(cutoff_dim)
+            self._trunc = cutoff_dim
+        if pure is not None:
+            self._pure = bool(pure)
+        self._phys = list(range(self._axes()))
+        self._pos = list(range(self._axes()))
+        self._alloc()
         L.call("b200_fill_zero", _ptr(self._buf), self._buf.numel(), self._stream())
         if self._rank == 0:
             L.call("b200_set_element", _ptr(self._buf), 0, 1.0, 0.0, self._stream())
         self._pending = {}
         self._opq = []
-        self._phys = list(range(self._num_modes))
-        self._pos = list(range(self._num_modes))
         self._untouched = set(range(self._num_modes))
         self._inactive = set()
         self._fresh = True  # still |0..0>: the first flush may choose which modes start out sharded
@@ -157,24 +226,48 @@ class ShardedCircuit(DeviceCircuit):
     def _tile_mode(self):
         return False
 
+    # Queue entries name TENSOR AXES (mode m for kets; 2m = ket, 2m+1 = bra for density matrices): that
+    # is what the exchange planner and the kernels work on.  A mixed-state gate is two entries, U on the
+    # ket axes and conj(U) on the bra axes, which the planner may schedule around different exchanges.
     def _emit_dense(self, U, mode):
-        self._opq.append(S.Op(S.KIND_SINGLE, (mode,), U, 0, self._trunc ** 2))
+        sz = self._trunc ** 2
+        if self._pure:
+            self._opq.append(S.Op(S.KIND_SINGLE, (mode,), U, 0, sz))
+        else:
+            self._opq.append(S.Op(S.KIND_SINGLE, (2 * mode,), U, 0, sz))
+            self._opq.append(S.Op(S.KIND_SINGLE, (2 * mode + 1,), U, 1, sz))
 
     def _emit_diags(self, items):
         for d, mode in items:
-            self._opq.append(S.Op(S.KIND_DIAG, (mode,), d, 0, self._trunc, 0.2))
+            axes = (mode,) if self._pure else (2 * mode, 2 * mode + 1)
+            op = S.Op(S.KIND_DIAG, axes, d, 0, self._trunc, 0.2)
+            op.mode = mode
+            self._opq.append(op)
 
     def _emit_pair(self, G, rule, m1, m2):
-        self._opq.append(S.Op(rule, (m1, m2), G, 0, L.packed_size(self._trunc)))
+        sz = L.packed_size(self._trunc)
+        if self._pure:
+            self._opq.append(S.Op(rule, (m1, m2), G, 0, sz))
+        else:
+            self._opq.append(S.Op(rule, (2 * m1, 2 * m2), G, 0, sz))
+            self._opq.append(S.Op(rule, (2 * m1 + 1, 2 * m2 + 1), G, 1, sz))
 
     def cross_kerr_interaction(self, kappa, mode1, mode2):
         raise NotImplementedError("cross_kerr_interaction on a sharded b200fock circuit")
+
+    def loss(self, T, mode):
+        """circuit.py:617-621 as ONE queued pair operator on the (ket, bra) axes of the mode."""
+        self._flush([mode])
+        self._touch(mode)
+        self._to_mixed()
+        G = self._gen2(L.CHANNEL_LOSS, T)
+        self._opq.append(S.Op(S.KIND_DIFF, (2 * mode, 2 * mode + 1), G, 0, L.packed_size(self._trunc)))
 
     def _exec(self, op):
         if op.kind == S.KIND_SINGLE:
             self._k_gate1(op.table, op.axes[0], op.conj)
         elif op.kind == S.KIND_DIAG:
-            self._k_diag_multi([(op.table, op.axes[0])])
+            self._k_diag_multi([(op.table, op.mode)])   # both axes of the mode for a density matrix
         else:
             self._k_gate2(op.table, op.kind, op.axes[0], op.axes[1], op.conj)
 
@@ -189,7 +282,7 @@ class ShardedCircuit(DeviceCircuit):
         # would cut the exchange into 16*D/p-byte (80 B) runs -- measured 110 GB/s instead of 590 GB/s
         # over NVLink -- and while the state is still |0..0> it may also pick the layout.
         replicated = []
-        if self._fresh and self._lazy_shard:
+        if self._fresh and self._lazy_shard and self._pure:
             # lazy vacuum: gates that act while at most k_max modes are entangled run replicated
             k_max = self._num_modes
             while self._trunc ** k_max * self._world > self._trunc ** self._num_modes:
@@ -363,7 +456,7 @@ class ShardedCircuit(DeviceCircuit):
         """Exchange without staging: for every source rank, ONE strided-gather launch reads that
         rank's block of the old layout straight out of its HBM over NVLink and writes it where it
         belongs in this rank's new shard (the other ping-pong buffer)."""
-        g, n, D = self._g, self._num_modes, self._trunc
+        g, n, D = self._g, self._axes(), self._trunc
         size = self._size()
         ls = [self._local_stride(p) for p in range(n)]
         sub = [D // p for p in self._ps]
@@ -420,7 +513,7 @@ class ShardedCircuit(DeviceCircuit):
 
     def _exchange(self, T):
         """Swap sharded axis k with local axis T[k] for every k."""
-        g, n = self._g, self._num_modes
+        g, n = self._g, self._axes()
         assert len(T) == g and all(t >= g for t in T)
         if self._p2p:
             self._exchange_p2p(T)
@@ -436,7 +529,7 @@ class ShardedCircuit(DeviceCircuit):
 
     def _exchange_nccl(self, T):
         """pack (strided gather) -> all_to_all_single -> unpack (strided gather)."""
-        g, n, D = self._g, self._num_modes, self._trunc
+        g, n, D = self._g, self._axes(), self._trunc
         size = self._size()
         if self._send is None:
             self._send, self._recv = self._new(size), self._new(size)
@@ -494,29 +587,49 @@ class ShardedCircuit(DeviceCircuit):
             prof.append(("exchange", 16 * size * (self._world - 1) // self._world, ev0, ev1))
 
     # ------------------------------------------------------------------ observation
+    def _walk(self, mode):
+        """How this rank walks the photon number of ``mode`` through its shard: the numbers
+        lo .. lo + ext - 1 sit at local offsets base + j * stride.  Kets: the rank's range of the mode's
+        axis.  Density matrices: the diagonal ket = bra, i.e. the intersection of the two axes' ranges
+        (ext = 0 when this rank holds no diagonal entry of the mode).  Returns (lo, ext, stride, base)."""
+        if self._pure:
+            lo, hi = self._range(mode)
+            return lo, hi - lo, self._stride(mode), 0
+        (kl, kh), (bl, bh) = self._range(2 * mode), self._range(2 * mode + 1)
+        lo, hi = max(kl, bl), min(kh, bh)
+        if hi <= lo:
+            return 0, 0, 0, 0
+        sk, sb = self._stride(2 * mode), self._stride(2 * mode + 1)
+        return lo, hi - lo, sk + sb, (lo - kl) * sk + (lo - bl) * sb
+
     def _norm_device(self):
+        """squared norm (kets) or trace (density matrices) of the whole state, on every rank"""
         self._flush()
         out = torch.zeros(1, dtype=torch.float64, device=self.device)
-        L.call("b200_norm2", _ptr(self._buf), self._size(), _ptr(out), _ptr(self._norm_part), self._stream())
+        if self._pure:
+            L.call("b200_norm2", _ptr(self._buf), self._size(), _ptr(out), _ptr(self._norm_part), self._stream())
+        else:
+            walks = [self._walk(m) for m in range(self._num_modes)]
+            if all(w[1] > 0 for w in walks):
+                self._gather(self._buf, None, out, [], [(w[1], w[2], 0) for w in walks], flags=L.FLAG_REAL_OUT,
+                             base=(sum(w[3] for w in walks), 0, 0))
         dist.all_reduce(out, group=self._pg)
         return out
 
     def norm(self):
-        return float(np.sqrt(self._norm_device().cpu().numpy()[0]))
+        v = float(self._norm_device().cpu().numpy()[0])
+        return float(np.sqrt(v)) if self._pure else v
 
     def element(self, n):
-        """<n|psi>: read on the owning rank, shared with all ranks."""
+        """<n|psi> (kets) or <n|rho|n> (density matrices): read on the owning rank, shared with all."""
         self._flush()
         idx, mine = 0, True
         for mode, x in enumerate(n):
-            pos = self._pos[mode]
-            x = int(x)
-            if pos < self._g:
-                sub = self._trunc // self._ps[pos]
-                if x // sub != self._digits[pos]:
-                    mine = False
-                x = x % sub
-            idx += x * self._local_stride(pos)
+            lo, ext, stride, base = self._walk(mode)
+            if not lo <= int(x) < lo + ext:
+                mine = False
+                break
+            idx += base + (int(x) - lo) * stride
         val = torch.zeros(2, dtype=torch.float64, device=self.device)
         if mine:
             val = torch.view_as_real(self._buf[idx:idx + 1]).reshape(2).clone()
@@ -525,9 +638,9 @@ class ShardedCircuit(DeviceCircuit):
         return np.array([v[0] + 1j * v[1]])
 
     def host_state(self):
-        """The whole ket on every rank's host (small states / tests only)."""
+        """The whole ket / density matrix on every rank's host (small states / tests only)."""
         self._flush()
-        g, n, D = self._g, self._num_modes, self._trunc
+        g, n, D = self._g, self._axes(), self._trunc
         parts = [torch.empty_like(self._buf) for _ in range(self._world)]
         dist.all_gather(parts, self._buf, group=self._pg)
         full = torch.stack(parts).cpu().numpy()
@@ -542,7 +655,8 @@ class ShardedCircuit(DeviceCircuit):
 
     def is_vacuum(self, tol):
         v = self.element([0] * self._num_modes)[0]
-        return bool(np.abs(np.abs(v) ** 2 - 1) <= tol)
+        fid = np.abs(v) ** 2 if self._pure else v.real
+        return bool(np.abs(fid - 1) <= tol)
 
     def snapshot(self):
         self._flush()
@@ -568,22 +682,23 @@ class ShardedCircuit(DeviceCircuit):
         every rank: each rank reduces its shard into its own block of the table, then one all-reduce of
         D^k doubles."""
         self._flush()
-        n, D, g = self._num_modes, self._trunc, self._g
-        k = len(keep)
+        D, k = self._trunc, len(keep)
         out = torch.zeros(D ** k, dtype=torch.float64, device=self.device)
-        oa, base_c = [], 0
-        for j, m in enumerate(keep):
-            pos, w = self._pos[m], D ** (k - 1 - j)
-            st = self._local_stride(pos)
-            if pos < g:
-                sub = D // self._ps[pos]
-                oa.append((sub, st, st, w))
-                base_c += self._digits[pos] * sub * w
+        walks = {m: self._walk(m) for m in range(self._num_modes)}
+        if all(w[1] > 0 for w in walks.values()):  # else: no diagonal entry of rho lives on this rank
+            sb = 1 if self._pure else 0             # kets: |psi|^2 = psi * conj(psi), same strides for B
+            oa, base_c = [], 0
+            for j, m in enumerate(keep):
+                lo, ext, stride, _ = walks[m]
+                oa.append((ext, stride, stride * sb, D ** (k - 1 - j)))
+                base_c += lo * D ** (k - 1 - j)
+            red = [(w[1], w[2], w[2] * sb) for m, w in walks.items() if m not in keep]
+            base_a = sum(w[3] for w in walks.values())
+            if self._pure:
+                self._gather(self._buf, self._buf, out, oa, red, flags=L.FLAG_CONJ_B | L.FLAG_REAL_OUT,
+                             base=(base_a, base_a, base_c))
             else:
-                oa.append((D, st, st, w))
-        kept_pos = {self._pos[m] for m in keep}
-        red = [(self._ext(p), self._local_stride(p), self._local_stride(p)) for p in range(n) if p not in kept_pos]
-        self._gather(self._buf, self._buf, out, oa, red, flags=L.FLAG_CONJ_B | L.FLAG_REAL_OUT, base=(0, 0, base_c))
+                self._gather(self._buf, None, out, oa, red, flags=L.FLAG_REAL_OUT, base=(base_a, 0, base_c))
         dist.all_reduce(out, group=self._pg)
         return out.view(1, -1)
 
@@ -591,12 +706,12 @@ class ShardedCircuit(DeviceCircuit):
         """all_fock_probs on every rank (small states only: D^n doubles per rank)."""
         return self.marginal_probs_device(list(range(self._num_modes)))
 
-    def _make_local(self, modes):
-        """Bring every mode of ``modes`` onto a whole (unsharded) axis."""
-        g, n = self._g, self._num_modes
-        if all(self._pos[m] >= g for m in modes):
+    def _make_local(self, axes):
+        """Bring every tensor axis of ``axes`` onto a whole (unsharded) position."""
+        g, n = self._g, self._axes()
+        if all(self._pos[a] >= g for a in axes):
             return
-        cand = [p for p in range(g, n) if self._phys[p] not in modes]
+        cand = [p for p in range(g, n) if self._phys[p] not in axes]
         if len(cand) < g:
             raise NotImplementedError("too many measured modes for a %d-rank sharded state" % self._world)
         cand.sort(key=lambda p: (p == n - 1, p))  # keep the innermost axis resident if possible
@@ -614,16 +729,17 @@ class ShardedCircuit(DeviceCircuit):
     def _project_reset(self, modes, values):
         """|0..0><x| on whole-axis modes: rank-local, out of place (into the other ping-pong buffer
         when the buffers are mapped into the peers)."""
-        n = self._num_modes
-        assert all(self._pos[m] >= self._g for m in modes)
+        n = self._axes()
+        axes_of = {m: self._mode_axes(m) for m in modes}
+        assert all(self._pos[a] >= self._g for ax in axes_of.values() for a in ax)
         self._fresh = False
         if self._p2p:
             out = self._bufs[1 - self._cur]
         else:
             out = self._get_scratch(self._buf.numel())
         L.call("b200_fill_zero", _ptr(out), out.numel(), self._stream())
-        base_a = sum(int(v) * self._stride(m) for m, v in zip(modes, values))
-        mpos = {self._pos[m] for m in modes}
+        base_a = sum(int(v) * self._stride(a) for m, v in zip(modes, values) for a in axes_of[m])
+        mpos = {self._pos[a] for ax in axes_of.values() for a in ax}
         oa = [(self._ext(p), self._local_stride(p), 0, self._local_stride(p)) for p in range(n) if p not in mpos]
         self._gather(self._buf, None, out, oa, base=(base_a, 0, 0))
         if self._p2p:
@@ -637,7 +753,7 @@ class ShardedCircuit(DeviceCircuit):
 
     def measure_fock(self, modes, select=None):
         self._flush()
-        self._make_local(list(modes))
+        self._make_local([a for m in modes for a in self._mode_axes(m)])
         return DeviceCircuit.measure_fock(self, modes, select)
 
     # ------------------------------------------------------------------ not sharded yet

@@ -42,30 +42,38 @@ def main():
              ("beamsplitter", 0.7, 0.2, 1, 0)]
     be = B200FockBackend()
     exchange = sys.argv[4] if len(sys.argv) > 4 else "auto"
-    lazy = len(sys.argv) > 5 and sys.argv[5] == "lazy"
-    be.begin_circuit(n, cutoff_dim=D, shard=True, exchange=exchange, lazy_vacuum=lazy)
+    flags = sys.argv[5:]
+    lazy = "lazy" in flags
+    # "mixed": the circuit starts as a density matrix; "loss": it starts pure and a LossChannel in the
+    # middle turns the sharded ket into a sharded density matrix
+    pure = "mixed" not in flags
+    if "mixed" in flags or "loss" in flags:
+        half = len(calls) // 2
+        calls = calls[:half] + [("loss", 0.8, 0), ("loss", 0.6, n - 1)] + calls[half:] + [("loss", 0.9, 1)]
+    be.begin_circuit(n, cutoff_dim=D, shard=True, exchange=exchange, lazy_vacuum=lazy, pure=pure)
     W.run_calls(be, calls + extra)
     st = be.state()
     from strawberryfields_b200 import sharding
 
     first_layout = list(next(iter(sharding._PLANS.values()))[0])  # layout the planner chose for |0..0>
-    ket = st.ket()
     ob = OracleBackend()
-    ob.begin_circuit(n, cutoff_dim=D)
+    ob.begin_circuit(n, cutoff_dim=D, pure=pure)
     W.run_calls(ob, calls + extra)
-    want = ob.state().data
-    err = float(np.abs(ket - want).max())
-    tr_err = abs(st.trace() - np.vdot(want, want).real)
+    ost = ob.state()
+    want = ost.data
+    assert st.is_pure == ost.is_pure
+    err = float(np.abs(st.data - want).max())
+    tr_err = abs(st.trace() - ost.trace())
     idx = [1] + [0] * (n - 2) + [2 % D]
-    fp_err = abs(st.fock_prob(idx) - np.abs(want[tuple(idx)]) ** 2)
+    fp_err = abs(st.fock_prob(idx) - ost.fock_prob(idx))
     # reductions: all_fock_probs (local reduce + all-reduce), then a seeded MeasureFock on a sharded and
-    # a local mode: same outcome and same post-measurement ket as the oracle
-    probs_err = float(np.abs(st.all_fock_probs() - np.abs(want) ** 2).max())
+    # a local mode: same outcome and same post-measurement state as the oracle
+    probs_err = float(np.abs(st.all_fock_probs() - ost.all_fock_probs()).max())
     np.random.seed(5)
     got_out = be.measure_fock([0, n - 1])
     np.random.seed(5)
     want_out = ob.measure_fock([0, n - 1])
-    post_err = float(np.abs(be.state().ket() - ob.state().data).max())
+    post_err = float(np.abs(be.state().data - ob.state().data).max())
     ok = bool(err < 1e-12 and tr_err < 1e-12 and fp_err < 1e-12 and probs_err < 1e-12
               and np.array_equal(got_out, want_out) and post_err < 1e-12)
     print(json.dumps({"rank": dist.get_rank(), "world": dist.get_world_size(), "err": err,

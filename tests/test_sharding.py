@@ -21,10 +21,11 @@ def _free_port():
     return port
 
 
-def _run(mode, world, n, D, exchange="auto", timeout=600, lazy=False):
+def _run(mode, world, n, D, exchange="auto", timeout=600, lazy=False, flags=()):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
-           os.path.join(ROOT, "tests", "dist_worker.py"), mode, str(n), str(D), exchange] + (["lazy"] if lazy else [])
+           os.path.join(ROOT, "tests", "dist_worker.py"), mode, str(n), str(D), exchange]
+    cmd += (["lazy"] if lazy else []) + list(flags)
     # start_new_session: on a timeout the whole torchrun process group is killed, nothing is left behind
     proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, start_new_session=True)
     try:
@@ -75,6 +76,17 @@ def test_sharded_lazy_vacuum_matches_oracle_gloo(world, n, D, exchange):
     measurement outcome (asserted by the worker on every rank)."""
     lines = _run("host", world, n, D, exchange, lazy=True)
     assert all(l["p2p"] == (exchange == "p2p") for l in lines)
+
+
+@pytest.mark.parametrize("world,n,D,exchange,flag", [(2, 3, 4, "auto", "loss"), (4, 4, 6, "p2p", "loss"),
+                                                     (4, 3, 4, "auto", "mixed"), (8, 5, 2, "auto", "mixed")])
+def test_sharded_density_matrices_match_oracle_gloo(world, n, D, exchange, flag):
+    """Sharded MIXED states: "mixed" starts as a density matrix (2n tensor axes, the leading ones sharded),
+    "loss" starts as a sharded ket that LossChannels turn into a sharded density matrix (all-gather of the
+    small ket, local outer product).  Gates become a ket-axis and a bra-axis entry of the exchange plan;
+    trace / probabilities / MeasureFock walk the ket = bra diagonal across the ranks.  Same density
+    matrix, reductions and measurement outcome as the oracle (asserted by the worker on every rank)."""
+    _run("host", world, n, D, exchange, flags=[flag])
 
 
 @pytest.mark.gpu
