@@ -515,6 +515,7 @@ class ShardedCircuit(DeviceCircuit):
         """Swap sharded axis k with local axis T[k] for every k."""
         g, n = self._g, self._axes()
         assert len(T) == g and all(t >= g for t in T)
+        self._own()  # the unpack writes in place: never into a buffer a state object still shares
         if self._p2p:
             self._exchange_p2p(T)
         else:
@@ -756,8 +757,37 @@ class ShardedCircuit(DeviceCircuit):
         self._make_local([a for m in modes for a in self._mode_axes(m)])
         return DeviceCircuit.measure_fock(self, modes, select)
 
+    def reduced_dm_device(self, keep):
+        """Reduced density matrix of the (sorted) modes ``keep`` -> complex128 [1, D^2k] with interleaved
+        (ket, bra) axes, the same on every rank (states.py:613-642).  The kept modes' axes are made local
+        first; every rank then contracts its part of the traced modes and D^2k numbers are all-reduced."""
+        self._flush()
+        self._make_local([a for m in keep for a in self._mode_axes(m)])
+        D, k, n = self._trunc, len(keep), self._num_modes
+        out = torch.zeros(D ** (2 * k), dtype=torch.complex128, device=self.device)
+        rest = [m for m in range(n) if m not in keep]
+        oa = []
+        for j, m in enumerate(keep):
+            axes = self._mode_axes(m)
+            wk, wb = D ** (2 * k - 1 - 2 * j), D ** (2 * k - 2 - 2 * j)
+            if self._pure:
+                oa += [(D, self._stride(axes[0]), 0, wk), (D, 0, self._stride(axes[0]), wb)]
+            else:
+                oa += [(D, self._stride(axes[0]), 0, wk), (D, self._stride(axes[1]), 0, wb)]
+        if self._pure:
+            red = [(self._ext(self._pos[m]), self._stride(m), self._stride(m)) for m in rest]
+            self._gather(self._buf, self._buf, out, oa, red, flags=L.FLAG_CONJ_B)
+        else:
+            walks = [self._walk(m) for m in rest]
+            if all(w[1] > 0 for w in walks):
+                self._gather(self._buf, None, out, oa, [(w[1], w[2], 0) for w in walks],
+                             base=(sum(w[3] for w in walks), 0, 0))
+        ri = torch.view_as_real(out)
+        dist.all_reduce(ri, group=self._pg)
+        return out.view(1, -1)
+
     # ------------------------------------------------------------------ not sharded yet
     def _unsupported(self, *a, **k):
         raise NotImplementedError("this operation is not available on a sharded b200fock circuit yet")
 
-    prepare_multimode = alloc = dealloc = measure_homodyne = reduced_dm_device = _unsupported
+    prepare_multimode = alloc = dealloc = measure_homodyne = _unsupported

@@ -68,12 +68,19 @@ def main():
     fp_err = abs(st.fock_prob(idx) - ost.fock_prob(idx))
     # reductions: all_fock_probs (local reduce + all-reduce), then a seeded MeasureFock on a sharded and
     # a local mode: same outcome and same post-measurement state as the oracle
-    probs_err = float(np.abs(st.all_fock_probs() - ost.all_fock_probs()).max())
+    probs_before = np.array(ost.all_fock_probs(), copy=True)
+    probs_err = float(np.abs(st.all_fock_probs() - probs_before).max())
+    # reduced density matrices (kept axes are exchanged in if they are sharded) and what builds on them
+    probs_err = max(probs_err, float(np.abs(st.reduced_dm([0, n - 1]) - ost.reduced_dm([0, n - 1])).max()),
+                    float(np.abs(np.array(st.mean_photon(1)) - np.array(ost.mean_photon(1))).max()),
+                    float(np.abs(np.array(st.quad_expectation(0, 0.3)) - np.array(ost.quad_expectation(0, 0.3))).max()))
     np.random.seed(5)
     got_out = be.measure_fock([0, n - 1])
     np.random.seed(5)
     want_out = ob.measure_fock([0, n - 1])
     post_err = float(np.abs(be.state().data - ob.state().data).max())
+    # the state object taken BEFORE the measurement still holds the pre-measurement state
+    post_err = max(post_err, float(np.abs(st.all_fock_probs() - probs_before).max()))
     ok = bool(err < 1e-12 and tr_err < 1e-12 and fp_err < 1e-12 and probs_err < 1e-12
               and np.array_equal(got_out, want_out) and post_err < 1e-12)
     print(json.dumps({"rank": dist.get_rank(), "world": dist.get_world_size(), "err": err,
