@@ -786,8 +786,21 @@ class ShardedCircuit(DeviceCircuit):
         dist.all_reduce(ri, group=self._pg)
         return out.view(1, -1)
 
+    def prepare_multimode(self, state, modes):
+        """Single-mode kets on modes that are still the untouched vacuum (the inputs of a boson-sampling
+        program): |v> = (|v><0|) |0>, so the preparation is queued as a rank-one single-mode operator and
+        costs what a gate costs.  Anything else needs a partial trace of the sharded state: not yet."""
+        modes = [modes] if isinstance(modes, int) else list(modes)
+        D = self._trunc
+        if len(modes) == 1 and modes[0] in self._untouched and self._pure and np.shape(state) == (D,):
+            tab = np.zeros((D, D), dtype=np.complex128)
+            tab[:, 0] = np.asarray(state, dtype=np.complex128)
+            self._queue_dense(self._upload_matrix(tab), modes[0])
+            return
+        self._unsupported()
+
     # ------------------------------------------------------------------ not sharded yet
     def _unsupported(self, *a, **k):
         raise NotImplementedError("this operation is not available on a sharded b200fock circuit yet")
 
-    prepare_multimode = alloc = dealloc = measure_homodyne = _unsupported
+    alloc = dealloc = measure_homodyne = _unsupported

@@ -51,13 +51,21 @@ def main():
         half = len(calls) // 2
         calls = calls[:half] + [("loss", 0.8, 0), ("loss", 0.6, n - 1)] + calls[half:] + [("loss", 0.9, 1)]
     be.begin_circuit(n, cutoff_dim=D, shard=True, exchange=exchange, lazy_vacuum=lazy, pure=pure)
+    ob = OracleBackend()
+    ob.begin_circuit(n, cutoff_dim=D, pure=pure)
+    if "fock" in flags:
+        # boson-sampling inputs: single photons in the first and the last mode.  The oracle prepares the
+        # whole product ket at once (its single-mode preparations would mix the state)
+        be.prepare_fock_state(1, 0)
+        be.prepare_fock_state(1, n - 1)
+        ket = np.zeros([D] * n, dtype=complex)
+        ket[(1,) + (0,) * (n - 2) + (1,)] = 1.0
+        ob.prepare_ket_state(ket, list(range(n)))
     W.run_calls(be, calls + extra)
     st = be.state()
     from strawberryfields_b200 import sharding
 
     first_layout = list(next(iter(sharding._PLANS.values()))[0])  # layout the planner chose for |0..0>
-    ob = OracleBackend()
-    ob.begin_circuit(n, cutoff_dim=D, pure=pure)
     W.run_calls(ob, calls + extra)
     ost = ob.state()
     want = ost.data

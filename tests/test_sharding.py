@@ -78,6 +78,13 @@ def test_sharded_lazy_vacuum_matches_oracle_gloo(world, n, D, exchange):
     assert all(l["p2p"] == (exchange == "p2p") for l in lines)
 
 
+def test_sharded_fock_inputs_gloo():
+    """Single-photon inputs (prepare_fock_state on untouched modes of a sharded ket) are queued as rank-one
+    single-mode operators; with lazy_vacuum they are product factors of the replicated prefix."""
+    _run("host", 4, 5, 6, "p2p", flags=["fock"])
+    _run("host", 2, 4, 4, "auto", flags=["lazy", "fock"])
+
+
 @pytest.mark.parametrize("world,n,D,exchange,flag", [(2, 3, 4, "auto", "loss"), (4, 4, 6, "p2p", "loss"),
                                                      (4, 3, 4, "auto", "mixed"), (8, 5, 2, "auto", "mixed")])
 def test_sharded_density_matrices_match_oracle_gloo(world, n, D, exchange, flag):
