@@ -55,9 +55,8 @@ def test_factor_world():
         factor_world(2, 7)
 
 
-@pytest.mark.parametrize("world,n,D,exchange", [(2, 4, 4, "auto"), (3, 4, 6, "auto"), (4, 5, 6, "auto"),
-                                                (8, 8, 2, "auto"), (4, 5, 6, "p2p"), (8, 8, 2, "p2p"),
-                                                (4, 5, 6, "push")])
+@pytest.mark.parametrize("world,n,D,exchange", [(2, 4, 4, "auto"), (3, 4, 6, "auto"), (4, 5, 6, "p2p"),
+                                                (8, 8, 2, "p2p"), (4, 5, 6, "push")])
 def test_sharded_circuit_matches_oracle_gloo(world, n, D, exchange):
     """exchange="auto" on the CPU is pack -> all_to_all_single -> unpack; "p2p" runs the peer-memory pull
     path (one strided gather per source rank, ping-pong buffers) with POSIX shared memory standing in
@@ -69,7 +68,7 @@ def test_sharded_circuit_matches_oracle_gloo(world, n, D, exchange):
         assert lines[0]["free_layout"]
 
 
-@pytest.mark.parametrize("world,n,D,exchange", [(4, 5, 6, "p2p"), (8, 8, 2, "auto")])
+@pytest.mark.parametrize("world,n,D,exchange", [(8, 8, 2, "auto")])
 def test_sharded_lazy_vacuum_matches_oracle_gloo(world, n, D, exchange):
     """lazy_vacuum=True on a sharded circuit: the prefix of the program that fits one rank runs replicated
     as a small lazy-vacuum circuit, then every rank writes its shard once; same ket, same
@@ -86,7 +85,7 @@ def test_sharded_fock_inputs_gloo():
 
 
 @pytest.mark.parametrize("world,n,D,exchange,flag", [(2, 3, 4, "auto", "loss"), (4, 4, 6, "p2p", "loss"),
-                                                     (4, 3, 4, "auto", "mixed"), (8, 5, 2, "auto", "mixed")])
+                                                     (8, 5, 2, "auto", "mixed")])
 def test_sharded_density_matrices_match_oracle_gloo(world, n, D, exchange, flag):
     """Sharded MIXED states: "mixed" starts as a density matrix (2n tensor axes, the leading ones sharded),
     "loss" starts as a sharded ket that LossChannels turn into a sharded density matrix (all-gather of the
