@@ -82,6 +82,8 @@ def main():
     probs_err = max(probs_err, float(np.abs(st.reduced_dm([0, n - 1]) - ost.reduced_dm([0, n - 1])).max()),
                     float(np.abs(np.array(st.mean_photon(1)) - np.array(ost.mean_photon(1))).max()),
                     float(np.abs(np.array(st.quad_expectation(0, 0.3)) - np.array(ost.quad_expectation(0, 0.3))).max()))
+    # state(modes=[...]): the reduced state in the requested (here: unsorted) mode order, on every rank
+    probs_err = max(probs_err, float(np.abs(be.state(modes=[n - 1, 1]).dm() - ob.state(modes=[n - 1, 1]).data).max()))
     np.random.seed(5)
     got_out = be.measure_fock([0, n - 1])
     np.random.seed(5)
