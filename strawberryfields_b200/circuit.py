@@ -1204,7 +1204,7 @@ class DeviceCircuit:
             probs /= np.sum(probs)
             probs[np.abs(probs) < 1e-10] = 0
             hist = np.random.multinomial(1, probs)
-            sample = q[list(hist).index(1)]
+            sample = self._agree_on(q[list(hist).index(1)])
 
         inf_sq = np.array([(-0.5) ** (n // 2) * np.sqrt(factorial(n)) / factorial(n // 2) if n % 2 == 0 else 0.0
                            for n in range(D)], dtype=C128)
@@ -1221,6 +1221,10 @@ class DeviceCircuit:
                self._stream())
         return np.array([[sample]])
 
+
+    def _agree_on(self, value):
+        """A sampled outcome every process must share (sharded circuits broadcast rank 0's draw)."""
+        return value
 
     def prepare_gkp(self, theta, phi, epsilon, ampl_cutoff, mode):
         """Finite-energy square-lattice GKP qubit state (circuit.py:803-812): a host-built ket."""

@@ -799,8 +799,19 @@ class ShardedCircuit(DeviceCircuit):
             return
         self._unsupported()
 
+    # homodyne (DeviceCircuit.measure_homodyne): the D x D marginal comes from reduced_dm_device above, the
+    # sample is rank 0's, and the projector |0><x_phi| is one more queued single-mode operator
+    def _agree_on(self, value):
+        t = torch.tensor([float(value)], dtype=torch.float64, device=self.device)
+        dist.broadcast(t, src=dist.get_global_rank(self._pg, 0) if self._pg is not None else 0, group=self._pg)
+        return float(t.item())
+
+    def _apply_dense_now(self, U, mode):
+        self._emit_dense(U, mode)
+        self._run_queue()
+
     # ------------------------------------------------------------------ not sharded yet
     def _unsupported(self, *a, **k):
         raise NotImplementedError("this operation is not available on a sharded b200fock circuit yet")
 
-    alloc = dealloc = measure_homodyne = _unsupported
+    alloc = dealloc = _unsupported

@@ -91,6 +91,23 @@ def main():
     post_err = float(np.abs(be.state().data - ob.state().data).max())
     # the state object taken BEFORE the measurement still holds the pre-measurement state
     post_err = max(post_err, float(np.abs(st.all_fock_probs() - probs_before).max()))
+    # homodyne on a mode that is entangled with the rest: same sample (rank 0's draw) and same conditional
+    # state as the UNSHARDED backend on the same double (the oracle has no homodyne; the single-process path
+    # is pinned by the reference's own homodyne tests, profiles/r01_reference_suite.md)
+    if mode == "host" and "fock" not in flags:
+        ref = B200FockBackend()
+        ref.begin_circuit(n, cutoff_dim=D, pure=pure)
+        W.run_calls(ref, calls + extra)
+        np.random.seed(5)
+        ref.measure_fock([0, n - 1])
+        for b in (be, ref):
+            b.beamsplitter(0.6, 0.4, 0, 1)
+        np.random.seed(9)
+        got_x = be.measure_homodyne(0.3, 1, num_bins=2000)
+        np.random.seed(9)
+        want_x = ref.measure_homodyne(0.3, 1, num_bins=2000)
+        post_err = max(post_err, float(np.abs(np.asarray(got_x) - np.asarray(want_x)).max()),
+                       float(np.abs(be.state().data - ref.state().data).max()))
     ok = bool(err < 1e-12 and tr_err < 1e-12 and fp_err < 1e-12 and probs_err < 1e-12
               and np.array_equal(got_out, want_out) and post_err < 1e-12)
     print(json.dumps({"rank": dist.get_rank(), "world": dist.get_world_size(), "err": err,
