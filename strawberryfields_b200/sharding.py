@@ -40,6 +40,7 @@ from .circuit import DeviceCircuit, _ptr
 
 
 _PLANS = {}  # (queue structure, layout, g, fresh) -> exchange plan: a repeated circuit is planned once
+_KIND_DIAG2 = 4  # two-axis diagonal (cross-Kerr): a queue kind next to scheduler.KIND_SINGLE/SUM/DIFF/DIAG
 
 
 def factor_world(P, D):
@@ -253,7 +254,14 @@ class ShardedCircuit(DeviceCircuit):
             self._opq.append(S.Op(rule, (2 * m1 + 1, 2 * m2 + 1), G, 1, sz))
 
     def cross_kerr_interaction(self, kappa, mode1, mode2):
-        raise NotImplementedError("cross_kerr_interaction on a sharded b200fock circuit")
+        """exp(i kappa n1 n2): a two-axis diagonal, queued like any other two-axis operator."""
+        self._touch(mode1, mode2)
+        self._flush([m for m in (mode1, mode2) if m in self._pending])  # keep program order on both modes
+        tab = self._gen_diag(L.DIAG_CROSS_KERR, kappa)
+        for conj, axes in enumerate(zip(self._mode_axes(mode1), self._mode_axes(mode2))):
+            op = S.Op(_KIND_DIAG2, axes, tab, conj, self._trunc ** 2)
+            op.kappa = kappa
+            self._opq.append(op)
 
     def loss(self, T, mode):
         """circuit.py:617-621 as ONE queued pair operator on the (ket, bra) axes of the mode."""
@@ -268,6 +276,8 @@ class ShardedCircuit(DeviceCircuit):
             self._k_gate1(op.table, op.axes[0], op.conj)
         elif op.kind == S.KIND_DIAG:
             self._k_diag_multi([(op.table, op.mode)])   # both axes of the mode for a density matrix
+        elif op.kind == _KIND_DIAG2:
+            self._k_diag_pair(op.table, op.axes[0], op.axes[1], op.conj)
         else:
             self._k_gate2(op.table, op.kind, op.axes[0], op.axes[1], op.conj)
 
@@ -325,6 +335,8 @@ class ShardedCircuit(DeviceCircuit):
                 rep._queue_dense(op.table, op.axes[0])
             elif op.kind == S.KIND_DIAG:
                 rep._queue_diag(op.table, op.axes[0])
+            elif op.kind == _KIND_DIAG2:
+                rep.cross_kerr_interaction(op.kappa, op.axes[0], op.axes[1])
             else:
                 rep._pair_gate(op.table, op.kind, op.axes[0], op.axes[1])
         active = list(rep._phys)

@@ -39,7 +39,7 @@ def main():
 
     calls = W.config2_circuit(n, seed=5)
     extra = [("mzgate", 0.4, 1.1, 0, n - 1), ("two_mode_squeeze", 0.2, 0.3, n - 1, 1), ("kerr_interaction", 0.1, 0),
-             ("beamsplitter", 0.7, 0.2, 1, 0)]
+             ("cross_kerr_interaction", 0.3, 0, n - 1), ("beamsplitter", 0.7, 0.2, 1, 0)]
     be = B200FockBackend()
     exchange = sys.argv[4] if len(sys.argv) > 4 else "auto"
     flags = sys.argv[5:]
