@@ -43,6 +43,10 @@ def main():
     be = B200FockBackend()
     exchange = sys.argv[4] if len(sys.argv) > 4 else "auto"
     flags = sys.argv[5:]
+    if "window7" in flags:  # plan the queue in windows of 7 entries (very long programs do that at 256)
+        from strawberryfields_b200 import sharding as _sh
+
+        _sh._PLAN_WINDOW = 7
     lazy = "lazy" in flags
     # "mixed": the circuit starts as a density matrix; "loss": it starts pure and a LossChannel in the
     # middle turns the sharded ket into a sharded density matrix

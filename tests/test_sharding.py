@@ -77,6 +77,12 @@ def test_sharded_lazy_vacuum_matches_oracle_gloo(world, n, D, exchange):
     assert all(l["p2p"] == (exchange == "p2p") for l in lines)
 
 
+def test_sharded_long_program_is_planned_in_windows_gloo():
+    """Queues longer than the planning window (256 entries; 7 here) are planned window by window, each
+    window starting from the layout the previous one ended in."""
+    _run("host", 4, 5, 6, "p2p", flags=["window7"])
+
+
 def test_sharded_fock_inputs_gloo():
     """Single-photon inputs (prepare_fock_state on untouched modes of a sharded ket) are queued as rank-one
     single-mode operators; with lazy_vacuum they are product factors of the replicated prefix."""
