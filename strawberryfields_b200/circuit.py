@@ -1059,31 +1059,44 @@ class DeviceCircuit:
         n, D, B = self._num_modes, self._trunc, self._B
         cur = self._buf
         per = self._size()
-        # strides of the modes still present in ``cur`` (one per mode for kets, (ket, bra) for dms)
-        strides = {m: [self._stride(ax) for ax in self._mode_axes(m)] for m in range(n)}
-        for m in sorted(range(n), key=lambda q: strides[q][0]):  # innermost first: contiguous reads
+        # (stride, lo, extent) of every tensor axis still present in ``cur``, per mode: one axis for kets,
+        # (ket, bra) for density matrices; lo / extent = the index range held here (whole axes unless sharded)
+        axes = {m: [(self._stride(ax),) + self._axis_range(ax) for ax in self._mode_axes(m)] for m in range(n)}
+        for m in sorted(range(n), key=lambda q: axes[q][0][0]):  # innermost first: contiguous reads
             v = np.asarray(vectors[m], dtype=C128).reshape(D)
+            (s0, lo0, e0) = axes[m][0]
             if self._pure:
-                w, red, flags = v, [(D, strides[m][0], 1)], L.FLAG_CONJ_B
+                w, red, flags, base_b = v, [(e0, s0, 1)], L.FLAG_CONJ_B, lo0
             else:
-                w, red, flags = np.multiply.outer(v.conj(), v), [(D, strides[m][0], D), (D, strides[m][1], 1)], 0
+                (s1, lo1, e1) = axes[m][1]
+                w, red, flags = np.multiply.outer(v.conj(), v), [(e0, s0, D), (e1, s1, 1)], 0
+                base_b = lo0 * D + lo1
             w = torch.from_numpy(np.ascontiguousarray(w)).to(self.device)
-            del strides[m]
-            rest = sorted(strides, key=lambda q: -strides[q][0])  # outermost first in the new tensor
-            width = len(self._mode_axes(0))
-            new_per = D ** (width * len(rest))
+            del axes[m]
+            rest = sorted(axes, key=lambda q: -axes[q][0][0])  # outermost first in the new tensor
+            new_per = 1
+            for q in rest:
+                for _, _, e in axes[q]:
+                    new_per *= e
             out = self._new(B * new_per)
             oa = [(B, per, 0, new_per)] if B > 1 else []
-            new_strides, k = {}, width * len(rest)
+            new_axes, acc = {}, new_per
             for q in rest:
-                new_strides[q] = []
-                for st in strides[q]:
-                    k -= 1
-                    oa.append((D, st, 0, D ** k))
-                    new_strides[q].append(D ** k)
-            self._gather(cur, w, out, oa, red, flags=flags)
-            cur, per, strides = out, new_per, new_strides
-        return cur
+                new_axes[q] = []
+                for st, lo, e in axes[q]:
+                    acc //= e
+                    oa.append((e, st, 0, acc))
+                    new_axes[q].append((acc, lo, e))
+            self._gather(cur, w, out, oa, red, flags=flags, base=(0, base_b, 0))
+            cur, per, axes = out, new_per, new_axes
+        return self._sum_over_ranks(cur)
+
+    def _axis_range(self, axis):
+        """(first index, extent) of tensor axis ``axis`` held by this process: the whole axis here"""
+        return 0, self._trunc
+
+    def _sum_over_ranks(self, t):
+        return t
 
     # ------------------------------------------------------------------ Fock measurement (circuit.py:623-711)
     def _project_reset(self, modes, values):

@@ -128,6 +128,14 @@ class ShardedCircuit(DeviceCircuit):
         sub = self._trunc // self._ps[pos]
         return self._digits[pos] * sub, (self._digits[pos] + 1) * sub
 
+    def _axis_range(self, axis):
+        lo, hi = self._range(axis)
+        return lo, hi - lo
+
+    def _sum_over_ranks(self, t):
+        dist.all_reduce(torch.view_as_real(t), group=self._pg)
+        return t
+
     def _canonicalize(self):  # the sharded layout is never canonical; readers go through _stride()
         return
 

@@ -85,7 +85,10 @@ def main():
     # reduced density matrices (kept axes are exchanged in if they are sharded) and what builds on them
     probs_err = max(probs_err, float(np.abs(st.reduced_dm([0, n - 1]) - ost.reduced_dm([0, n - 1])).max()),
                     float(np.abs(np.array(st.mean_photon(1)) - np.array(ost.mean_photon(1))).max()),
-                    float(np.abs(np.array(st.quad_expectation(0, 0.3)) - np.array(ost.quad_expectation(0, 0.3))).max()))
+                    float(np.abs(np.array(st.quad_expectation(0, 0.3)) - np.array(ost.quad_expectation(0, 0.3))).max()),
+                    abs(st.fidelity_coherent([0.2 * np.exp(0.5j * m) for m in range(n)])
+                        - ost.fidelity_coherent([0.2 * np.exp(0.5j * m) for m in range(n)])),
+                    abs(st.parity_expectation([0, n - 1]) - ost.parity_expectation([0, n - 1])))
     # state(modes=[...]): the reduced state in the requested (here: unsorted) mode order, on every rank
     probs_err = max(probs_err, float(np.abs(be.state(modes=[n - 1, 1]).dm() - ob.state(modes=[n - 1, 1]).data).max()))
     np.random.seed(5)
