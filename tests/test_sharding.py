@@ -118,13 +118,15 @@ def test_sharded_circuit_matches_oracle_on_gpus(exchange):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("exchange,lazy", [("push", False), ("p2p", True)])
-def test_sharded_paths_written_after_round1_on_gpus(exchange, lazy):
-    """The push form of the peer-memory exchange and the sharded lazy vacuum: host logic verified on the CPU
-    doubles above, first GPU run pending (round 1's GPU budget ended before they were written)."""
+@pytest.mark.parametrize("exchange,lazy,flags", [("push", False, ()), ("p2p", True, ()), ("p2p", False, ("loss",)),
+                                                 ("p2p", False, ("fock",))])
+def test_sharded_paths_written_after_round1_on_gpus(exchange, lazy, flags):
+    """The push form of the peer-memory exchange, the sharded lazy vacuum, sharded density matrices and Fock
+    inputs: host logic verified on the CPU doubles above, first GPU run pending (round 1's GPU budget ended
+    before they were written)."""
     import torch
 
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
-    lines = _run("gpu", 2, 5, 6, exchange, timeout=150, lazy=lazy)
+    lines = _run("gpu", 2, 4 if flags else 5, 6, exchange, timeout=150, lazy=lazy, flags=flags)
     assert all(l["p2p"] for l in lines)
