@@ -22,8 +22,6 @@ mzgate, two_mode_squeeze on pure states (vacuum input), scalar or per-batch-entr
 """
 from __future__ import annotations
 
-import ctypes as C
-
 import numpy as np
 import torch
 
