@@ -222,3 +222,34 @@ def test_tile_mode_fuses_gates_into_fewer_launches(monkeypatch, golden_dir):
     assert np.abs(ket - ref).max() < TOL
     assert set(log) == {"b200_apply_tile_pass"}
     assert len(log) < len(gl) / 2
+
+
+def test_wrong_strides_fail_on_the_host(monkeypatch):
+    """Every gather descriptor and gate launch is bounds-checked before it reaches the library: a
+    wrong stride, base offset or table raises B200Error instead of addressing memory outside its
+    tensor (an illegal address on the device)."""
+    import torch
+
+    from strawberryfields_b200 import circuit, lib
+
+    monkeypatch.setattr(lib, "_lib", FakeLib())
+    monkeypatch.setattr(circuit, "_TEST_HOST_MODE", True)
+    c = circuit.DeviceCircuit(3, 4)
+    n = c._buf.numel()
+    out = torch.zeros(n, dtype=torch.complex128)
+    c._gather(c._buf, None, out, [(n, 1, 0, 1)])                                  # fine
+    with pytest.raises(lib.B200Error, match="operand A"):
+        c._gather(c._buf, None, out, [(n, 2, 0, 1)])                              # reads past the state
+    with pytest.raises(lib.B200Error, match="operand C"):
+        c._gather(c._buf, None, out, [(n, 1, 0, 1)], base=(0, 0, 1))              # writes past the output
+    with pytest.raises(lib.B200Error, match="operand A"):
+        c._gather(c._buf, None, out[:1], [], [(n, 1, 0)], base=(-1, 0, 0))        # negative offset
+    with pytest.raises(lib.B200Error, match="operand B"):
+        c._gather(c._buf, out[:4], out, [(n, 1, 1, 1)])                           # second operand too short
+    U = c._gen1(lib.GATE_DISPLACEMENT, 0.1, 0.2)
+    c._k_gate1(U, 1, 0)                                                           # fine
+    with pytest.raises(lib.B200Error, match="gate table"):
+        c._k_gate1(U.reshape(-1)[:8].view(1, 2, 4), 1, 0)                         # truncated table
+    c._buf = c._buf[: n // 2]
+    with pytest.raises(lib.B200Error, match="state buffer"):
+        c._k_gate1(U, 1, 0)                                                       # buffer smaller than the state
