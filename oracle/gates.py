@@ -284,6 +284,23 @@ def displaced_squeezed_state(r_d, phi_d, r_s, phi_s, D):
     return N * vec
 
 
+def square_gkp_state(theta, phi, epsilon, ampl_cutoff, D):
+    """fockbackend/ops.py:518-596: cos(theta/2)|0>_gkp + e^{-i phi} sin(theta/2)|1>_gkp, each basis
+    state a comb of displaced squeezed states (teeth t = -z_max..z_max at sqrt(pi/2)(2t+k)/cosh(eps),
+    weights exp(-pi/2 tanh(eps) (k+2t)^2), squeezing r = -log(tanh eps)/2), normalised at the end."""
+    z_max = int(np.ceil(np.sqrt(-0.25 / np.pi * np.log(ampl_cutoff) / np.tanh(epsilon))))
+    r = -0.5 * np.log(np.tanh(epsilon))
+    basis = []
+    for k in (0, 1):
+        ket = np.zeros(D, dtype=C128)
+        for t in range(-z_max, z_max + 1):
+            ket = ket + np.exp(-0.5 * np.pi * np.tanh(epsilon) * (k + 2 * t) ** 2) * displaced_squeezed_state(
+                np.sqrt(0.5 * np.pi) * (2 * t + k) / np.cosh(epsilon), 0, r, 0, D)
+        basis.append(ket)
+    ket = np.cos(theta / 2) * basis[0] + np.sin(theta / 2) * np.exp(-1j * phi) * basis[1]
+    return ket / np.linalg.norm(ket)
+
+
 def thermal_state(nbar, D):
     if nbar == 0:
         v = fock_state(0, D)

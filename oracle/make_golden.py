@@ -78,8 +78,11 @@ def main():
     import scripts
 
     os.makedirs(GOLD, exist_ok=True)
+    only = sys.argv[1:]  # e.g. `python -m oracle.make_golden homodyne`: just the scripts whose name matches
     for sc in scripts.all_scripts():
         name = sc[0]
+        if only and not any(o in name for o in only):
+            continue
         be = FockBackend()
         rets, st = scripts.run_script(be, sc)
         data = np.ascontiguousarray(st.data)
@@ -95,6 +98,8 @@ def main():
         np.savez_compressed(os.path.join(GOLD, f"ref_{name}.npz"), **out)
         print("wrote", name, {k: getattr(v, "shape", None) for k, v in out.items()})
 
+    if only:
+        return
     # compiled BASELINE-shaped circuits: gate list from the reference front end,
     # final ket from the reference backend through sf.Engine
     for N, D in ((4, 6), (5, 5)):

@@ -205,6 +205,26 @@ def measure_postselect(D, pure):
     return (f"measure_select_d{D}_{'pure' if pure else 'mixed'}", 3, D, pure, calls)
 
 
+def homodyne_gkp(D, pure):
+    """GKP preparation and homodyne measurements (circuit.py:713-812): a sampled outcome on an entangled
+    mode, a post-selected one, and a second sampled one; ``num_bins`` keeps the host grid small."""
+    calls = [
+        C("prepare_gkp", [0.6, 0.4], 0.35, 1e-3, mode=0),
+        C("squeeze", 0.3, 0.2, 1),
+        C("beamsplitter", 0.6, 0.3, 0, 1),
+        C("two_mode_squeeze", 0.2, 0.1, 1, 2),
+        C("seed", 21),
+        C("measure_homodyne", 0.4, 1, num_bins=5000),
+        C("displacement", 0.2, 0.3, 2),
+        C("measure_homodyne", 0.0, 0, select=0.37),
+        C("rotation", 0.5, 2),
+        C("seed", 4),
+        C("measure_homodyne", 1.1, 2, num_bins=5000),
+        C("beamsplitter", 0.3, 0.1, 2, 0),
+    ]
+    return (f"homodyne_gkp_d{D}_{'pure' if pure else 'mixed'}", 3, D, pure, calls)
+
+
 def all_scripts():
     return [
         boson_sampling(5),
@@ -223,6 +243,8 @@ def all_scripts():
         preparations(4),
         measure_postselect(6, True),
         measure_postselect(5, False),
+        homodyne_gkp(8, True),
+        homodyne_gkp(6, False),
     ]
 
 
