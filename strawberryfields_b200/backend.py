@@ -13,7 +13,10 @@ stand-alone through the same backend API.
 Extra ``begin_circuit`` options: ``batch_size`` (leading batch axis, TF-backend
 semantics -- the reference fock backend ignores it), ``strict_purity`` (follow
 the reference's switch to a mixed representation on single-mode preparations),
-``fuse`` (lazy gate queue, default on).
+``fuse`` (lazy gate queue: ``True``/``"fold"`` default, ``"tile"``, ``False``), ``lazy_vacuum``
+(untouched modes stay product factors; off by default), ``device``, and for several
+GPUs ``shard`` (``True`` or a ``torch.distributed`` group: one state over all ranks, kets and
+density matrices) with ``exchange`` (``"auto"`` | ``"p2p"`` | ``"push"`` | ``"nccl"``).
 """
 from __future__ import annotations
 
