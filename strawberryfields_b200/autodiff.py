@@ -369,6 +369,46 @@ class _CircuitFn(torch.autograd.Function):
 
 
 # ---------------------------------------------------------------------------------------------
+# Differentiable read-outs of the ket a TorchCircuit returns (plain torch reductions: the loss side of a
+# training loop, cf. state.ket() / trace() / mean_photon() in the reference's TF examples).  ``ket`` is
+# [D]*n or [B] + [D]*n; ``batched`` says which.
+def _as_batch(ket, batched):
+    return ket if batched else ket.unsqueeze(0)
+
+
+def fock_probs(ket, batched=False):
+    """|<n|psi>|^2, same shape as ``ket``"""
+    return ket.real ** 2 + ket.imag ** 2
+
+
+def trace(ket, batched=False):
+    """squared norm (the probability kept inside the cutoff), one value per batch entry"""
+    p = fock_probs(_as_batch(ket, batched))
+    out = p.reshape(p.shape[0], -1).sum(dim=1)
+    return out if batched else out[0]
+
+
+def mean_photon(ket, mode, batched=False):
+    """(mean, variance) of the photon number of ``mode``"""
+    p = fock_probs(_as_batch(ket, batched))
+    n_modes = p.dim() - 1
+    marg = p.sum(dim=[1 + m for m in range(n_modes) if m != mode])
+    n = torch.arange(marg.shape[1], dtype=marg.dtype, device=marg.device)
+    mean = (marg * n).sum(dim=1)
+    var = (marg * n ** 2).sum(dim=1) - mean ** 2
+    return (mean, var) if batched else (mean[0], var[0])
+
+
+def fidelity(ket, target, batched=False):
+    """|<target|psi>|^2 for a target ket of the unbatched shape"""
+    k = _as_batch(ket, batched)
+    t = torch.as_tensor(target, dtype=k.dtype, device=k.device).reshape(-1)
+    ov = (k.reshape(k.shape[0], -1) * t.conj()).sum(dim=1)
+    out = ov.real ** 2 + ov.imag ** 2
+    return out if batched else out[0]
+
+
+# ---------------------------------------------------------------------------------------------
 # CV quantum neural network layers -- the parameter layout of
 # /root/reference/examples/quantum_neural_network.py:14-85 (BASELINE config 4)
 def qnn_interferometer_size(N):

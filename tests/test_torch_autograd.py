@@ -264,6 +264,43 @@ def test_checkpoint_thinning_gives_the_same_gradients(every, make):
     assert np.abs(grads[0] - grads[1]).max() < 1e-13
 
 
+def test_readouts_match_the_oracle_and_differentiate(make):
+    """trace / mean_photon / fidelity / fock_probs of the returned ket: oracle values, and a gradient that
+    flows through them (finite differences)."""
+    from strawberryfields_b200 import autodiff as A
+
+    n, D = 2, 7
+    r = torch.tensor(0.4, dtype=torch.float64, requires_grad=True)
+
+    def run(rv):
+        prog = make(n, D)
+        prog.displacement(rv, 0.3, 0)
+        prog.squeeze(0.25, 0.1, 1)
+        prog.beamsplitter(0.5, 0.2, 0, 1)
+        return prog.ket()
+
+    ket = run(r)
+    ob = OracleBackend()
+    ob.begin_circuit(n, cutoff_dim=D)
+    ob.displacement(0.4, 0.3, 0)
+    ob.squeeze(0.25, 0.1, 1)
+    ob.beamsplitter(0.5, 0.2, 0, 1)
+    ost = ob.state()
+    assert abs(A.trace(ket).item() - ost.trace()) < TOL
+    got = A.mean_photon(ket, 1)
+    assert np.abs(np.array([got[0].item(), got[1].item()]) - np.array(ost.mean_photon(1))).max() < TOL
+    assert np.abs(A.fock_probs(ket).detach().cpu().numpy() - ost.all_fock_probs()).max() < TOL
+    target = np.zeros((D, D), dtype=complex)
+    target[1, 0] = 1.0
+    assert abs(A.fidelity(ket, target).item() - ost.fock_prob([1, 0])) < TOL
+    loss = A.mean_photon(ket, 0)[0] + 0.5 * A.trace(ket)
+    loss.backward()
+    h = 1e-6
+    with torch.no_grad():
+        vals = [(A.mean_photon(run(0.4 + s * h), 0)[0] + 0.5 * A.trace(run(0.4 + s * h))).item() for s in (1, -1)]
+    assert abs(r.grad.item() - (vals[0] - vals[1]) / (2 * h)) < 1e-7
+
+
 def test_constant_prefix_and_second_backward(make):
     """Gates before the first differentiable one keep no checkpoint; a second backward pass over the
     same graph is refused (the checkpoints are consumed)."""
