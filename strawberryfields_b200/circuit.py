@@ -754,9 +754,12 @@ class DeviceCircuit:
         self._set_identity_layout()
 
     # ------------------------------------------------------------------ norm (circuit.py:367-371)
-    def _norm_device(self):
-        """squared norm (pure) or trace (mixed) per batch entry, as a device float64 tensor [B]."""
-        self._flush()
+    def _norm_device(self, materialize=True):
+        """squared norm (pure) or trace (mixed) per batch entry, as a device float64 tensor [B].
+        ``materialize=False``: of the device tensor as it is -- right after a measurement the modes outside
+        it are plain |0> factors of norm one (lazy vacuum)."""
+        if materialize:
+            self._flush()
         B, per = self._B, self._size()
         out = torch.zeros(B, dtype=torch.float64, device=self.device)
         if self._pure:
@@ -765,7 +768,8 @@ class DeviceCircuit:
                        C.c_void_p(out.data_ptr() + 8 * b), _ptr(self._norm_part), self._stream())
         else:
             n, D = self._num_modes, self._trunc
-            red = [(D, self._stride(2 * i) + self._stride(2 * i + 1), 0) for i in range(n)]
+            red = [(D, self._stride(2 * i) + self._stride(2 * i + 1), 0) for i in range(n)
+                   if i not in self._inactive]
             oa = [(B, per, 0, 1)] if B > 1 else []
             self._gather(self._buf, None, out, oa, red, flags=L.FLAG_REAL_OUT)
         return out
@@ -1102,12 +1106,27 @@ class DeviceCircuit:
     def _project_reset(self, modes, values):
         """|0..0><x| on ``modes`` (ops.py:179-198), out of place."""
         D = self._trunc
-        out = self._get_scratch(self._buf.numel())
-        L.call("b200_fill_zero", _ptr(out), out.numel(), self._stream())
         base_a = 0
         for m, v in zip(modes, values):
             for ax in self._mode_axes(m):
                 base_a += int(v) * self._stride(ax)
+        if self._lazy_opt and self._fuse == "fold" and not self._batched:
+            # lazy vacuum: the measured modes are |0> and unentangled again, so they simply leave the device
+            # tensor (which shrinks by D per axis) and become product factors until a gate needs them
+            gone = {ax for m in modes for ax in self._mode_axes(m)}
+            keep = [ax for ax in self._phys if ax not in gone]
+            out = self._new(D ** len(keep))
+            oa = [(D, self._stride(ax), 0, D ** (len(keep) - 1 - j)) for j, ax in enumerate(keep)]
+            self._gather(self._buf, None, out, oa, base=(base_a, 0, 0))
+            self._buf, self._shared, self._scratch = out, False, None
+            self._phys = keep
+            self._pos = [None] * self._axes()
+            for p, ax in enumerate(keep):
+                self._pos[ax] = p
+            self._inactive.update(modes)
+            return
+        out = self._get_scratch(self._buf.numel())
+        L.call("b200_fill_zero", _ptr(out), out.numel(), self._stream())
         oa = []
         for m in range(self._num_modes):
             if m in modes:
@@ -1122,7 +1141,7 @@ class DeviceCircuit:
 
     def _renormalise(self):
         self._own()
-        nrm = self._norm_device()
+        nrm = self._norm_device(materialize=False)  # only ever called right after a flush + projection
         if float(nrm[0].item()) == 0:
             raise ZeroDivisionError("Measurement has zero probability.")
         L.call("b200_scale", _ptr(self._buf), self._buf.numel(), 1.0, 0.0, _ptr(nrm), 1 if self._pure else 0,

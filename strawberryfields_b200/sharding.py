@@ -630,7 +630,7 @@ class ShardedCircuit(DeviceCircuit):
         sk, sb = self._stride(2 * mode), self._stride(2 * mode + 1)
         return lo, hi - lo, sk + sb, (lo - kl) * sk + (lo - bl) * sb
 
-    def _norm_device(self):
+    def _norm_device(self, materialize=True):
         """squared norm (kets) or trace (density matrices) of the whole state, on every rank"""
         self._flush()
         out = torch.zeros(1, dtype=torch.float64, device=self.device)

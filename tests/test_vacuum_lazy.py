@@ -95,6 +95,38 @@ def test_observation_between_gates(backend):
     assert np.abs(be.state().ket() - ob.state().data).max() < TOL
 
 
+def test_measured_modes_leave_the_tensor(backend):
+    """After MeasureFock the measured modes are |0> and unentangled: they drop out of the device tensor
+    (it shrinks by D per mode) and come back as factors when a later gate needs them."""
+    n, D = 4, 5
+    be, ob = backend(), OracleBackend()
+    for b in (be, ob):
+        b.begin_circuit(n, cutoff_dim=D)
+        b.squeeze(0.4, 0.1, 0)
+        b.beamsplitter(0.6, 0.2, 0, 1)
+        b.beamsplitter(0.5, 0.1, 1, 2)
+        b.two_mode_squeeze(0.3, 0.2, 2, 3)
+    np.random.seed(2)
+    got = be.measure_fock([3, 1])
+    np.random.seed(2)
+    want = ob.measure_fock([3, 1])
+    assert np.array_equal(got, want)
+    assert be.circuit._size() == D ** 2 and be.circuit._inactive == {1, 3}
+    for b in (be, ob):
+        b.displacement(0.2, 0.3, 1)          # folds into the factor of mode 1
+        b.beamsplitter(0.4, 0.3, 0, 2)       # runs on the D^2 tensor
+    assert be.circuit._size() == D ** 2
+    for b in (be, ob):
+        b.beamsplitter(0.7, 0.1, 1, 0)       # mode 1 comes back
+    assert be.circuit._size() == D ** 3
+    np.random.seed(3)
+    got = be.measure_fock([0, 1, 2, 3])      # everything measured: a one-amplitude tensor
+    np.random.seed(3)
+    want = ob.measure_fock([0, 1, 2, 3])
+    assert np.array_equal(got, want) and be.circuit._size() == 1
+    assert np.abs(be.state().ket() - ob.state().data).max() < TOL
+
+
 def test_reset_and_loss(backend):
     """reset() returns to the factored vacuum; a loss channel materialises and mixes."""
     n, D = 3, 5
