@@ -1243,9 +1243,33 @@ class DeviceCircuit:
         alpha = sample * np.sqrt(w / 2)
         disp = self._gen1(L.GATE_DISPLACEMENT, float(np.abs(alpha)), float(np.angle(alpha)))[0].cpu().numpy()
         eig = (np.exp(1j * phi * np.arange(D))[:, None] * disp) @ inf_sq
+        self._touch(mode)
+        if self._lazy_opt and self._fuse == "fold" and type(self) is DeviceCircuit:
+            # lazy vacuum: |0><x_phi| leaves the mode in |0>, unentangled -- contract the mode with <x_phi|
+            # (one read of the state, a D-times smaller write) and let it leave the device tensor
+            axes = self._mode_axes(mode)
+            keep = [ax for ax in self._phys if ax not in axes]
+            out = self._new(D ** len(keep))
+            oa = [(D, self._stride(ax), 0, D ** (len(keep) - 1 - j)) for j, ax in enumerate(keep)]
+            if self._pure:
+                w, red, flags = eig, [(D, self._stride(axes[0]), 1)], L.FLAG_CONJ_B
+            else:
+                w = np.multiply.outer(eig.conj(), eig)
+                red, flags = [(D, self._stride(axes[0]), D), (D, self._stride(axes[1]), 1)], 0
+            w = torch.from_numpy(np.ascontiguousarray(w)).to(self.device)
+            self._gather(self._buf, w, out, oa, red, flags=flags)
+            self._buf, self._shared, self._scratch = out, False, None
+            self._phys = keep
+            self._pos = [None] * self._axes()
+            for p, ax in enumerate(keep):
+                self._pos[ax] = p
+            self._inactive.add(mode)
+            nrm = self._norm_device(materialize=False)
+            L.call("b200_scale", _ptr(self._buf), self._buf.numel(), 1.0, 0.0, _ptr(nrm), 1 if self._pure else 0,
+                   self._stream())
+            return np.array([[sample]])
         proj = np.zeros((D, D), dtype=C128)
         proj[0, :] = eig.conj()
-        self._touch(mode)
         self._apply_dense_now(self._upload_matrix(proj), mode)
         self._own()
         nrm = self._norm_device()
