@@ -48,6 +48,10 @@ def host_backend(request, monkeypatch):
 def test_script_matches_reference_fixture(script, fuse, host_backend, golden_dir, request):
     if script[0] == "boson_sampling_d7" and request.node.callspec.params["host_backend"] == "host":
         pytest.skip("large for the numpy double; run on the GPU")
+    if script[0].startswith("homodyne_gkp") and request.node.callspec.params["host_backend"] == "gpu":
+        # written after round 1's GPU budget ended: their first GPU run is in tests/test_vacuum_lazy.py, the
+        # last file of the suite, so that a surprise there cannot hide the results of the validated tests
+        pytest.skip("GPU variant runs in tests/test_vacuum_lazy.py::test_homodyne_scripts_eager")
     ref = np.load(os.path.join(golden_dir, f"ref_{script[0]}.npz"))
     rets, st = scripts.run_script(host_backend(strict_purity=True, fuse=fuse), script)
     assert bool(ref["pure"]) == st.is_pure

@@ -95,6 +95,24 @@ def test_observation_between_gates(backend):
     assert np.abs(be.state().ket() - ob.state().data).max() < TOL
 
 
+@pytest.mark.parametrize("fuse", [True, "tile", False])
+@pytest.mark.parametrize("script", [scripts.homodyne_gkp(8, True), scripts.homodyne_gkp(6, False)],
+                         ids=lambda s: s[0])
+def test_homodyne_scripts_eager(script, fuse, backend, golden_dir):
+    """GKP preparation + homodyne on the EAGER path (lazy_vacuum=False), every gate-queue mode: identical
+    samples and final state as the reference fixture.  (Lives here, in the last file of the suite, because
+    its GPU variant has not run yet -- see tests/test_backend.py.)"""
+    ref = np.load(os.path.join(golden_dir, f"ref_{script[0]}.npz"))
+    rets, st = scripts.run_script(backend(strict_purity=True, fuse=fuse, lazy_vacuum=False), script)
+    assert bool(ref["pure"]) == st.is_pure
+    if "probs" in ref:
+        assert np.abs(st.all_fock_probs() - ref["probs"]).max() < TOL
+    else:
+        assert np.abs(st.data - ref["data"]).max() < TOL
+    for i, r in enumerate(rets):
+        assert np.array_equal(r, ref[f"ret{i}"])
+
+
 def test_measured_modes_leave_the_tensor(backend):
     """After MeasureFock the measured modes are |0> and unentangled: they drop out of the device tensor
     (it shrinks by D per mode) and come back as factors when a later gate needs them."""
