@@ -59,6 +59,65 @@ class DeviceParams:
         self.nbatch = 1 if tensor.dim() == 1 else int(tensor.shape[1])
 
 
+class TableCache:
+    """Parameter-keyed cache of device gate tables -- what the reference's ten ``functools.lru_cache``
+    decorators do for its host matrices (``fockbackend/ops.py:208-343``), extended to the tables the
+    fold stage derives from them (products of same-mode gates, diagonals folded into a dense or a
+    two-mode table).  Every table carries a *recipe*: a hashable description of how it was built
+    (generator kind + host parameters, or an operation on other recipes).  A repeated circuit therefore
+    launches no generator, compose or fold kernel at all: each gate pass finds its table by recipe.
+    Tables built from device-resident parameters (``DeviceParams``) have no recipe and are never cached.
+    Cached tables are shared and must never be written in place."""
+
+    def __init__(self, max_bytes=256 << 20):
+        from collections import OrderedDict
+
+        self._d = OrderedDict()
+        self._bytes = 0
+        self.max_bytes = max_bytes
+        self.hits = 0
+        self.misses = 0
+        self.enabled = True
+
+    def get(self, recipe, build):
+        """the table of ``recipe`` (built with ``build()`` on a miss); ``recipe is None``: always build"""
+        if recipe is None or not self.enabled:
+            t = build()
+            t._recipe = recipe
+            return t
+        t = self._d.get(recipe)
+        if t is not None:
+            self._d.move_to_end(recipe)
+            self.hits += 1
+            return t
+        self.misses += 1
+        t = build()
+        t._recipe = recipe
+        self._d[recipe] = t
+        self._bytes += t.numel() * t.element_size()
+        while self._bytes > self.max_bytes and len(self._d) > 1:
+            _, old = self._d.popitem(last=False)
+            self._bytes -= old.numel() * old.element_size()
+        return t
+
+    def clear(self):
+        self._d.clear()
+        self._bytes = 0
+
+
+TABLES = TableCache()
+
+
+def _recipe(t):
+    return getattr(t, "_recipe", None) if t is not None else 0
+
+
+def _derived(op, *parts):
+    """recipe of a table derived from other tables (None as soon as one input has none)"""
+    rs = tuple(p if isinstance(p, (int, str)) else _recipe(p) for p in parts)
+    return None if any(r is None for r in rs) else (op,) + rs
+
+
 class DeviceCircuit:
     """GPU mirror of ``fockbackend.circuit.Circuit``."""
 
@@ -255,14 +314,15 @@ class DeviceCircuit:
 
     # ------------------------------------------------------------------ gate tables
     def _params(self, *ps):
-        """scalars or length-B arrays -> (nbatch, scalars, device params or None)"""
+        """scalars or length-B arrays -> (nbatch, scalars, device params or None, cache key or None)"""
         if isinstance(ps[0], DeviceParams):
             if ps[0].nbatch not in (1, self._B):
                 raise ValueError("DeviceParams batch does not match the circuit's batch_size")
-            return ps[0].nbatch, [0.0, 0.0], ps[0].tensor
+            return ps[0].nbatch, [0.0, 0.0], ps[0].tensor, None
         arrs = [np.asarray(p, dtype=np.float64) for p in ps]
         if all(a.ndim == 0 for a in arrs):
-            return 1, [float(a) for a in arrs] + [0.0] * (2 - len(arrs)), None
+            sc = [float(a) for a in arrs] + [0.0] * (2 - len(arrs))
+            return 1, sc, None, tuple(sc)
         if not self._batched:
             raise ValueError("array-valued gate parameters need a batched circuit (batch_size=...)")
         full = np.zeros((2, self._B), dtype=np.float64)
@@ -273,38 +333,57 @@ class DeviceCircuit:
                 full[i, :] = a
             else:
                 raise ValueError("gate parameter must be a scalar or have shape (batch_size,)")
-        dev = torch.from_numpy(full).to(self.device)
-        return self._B, [0.0, 0.0], dev
+        return self._B, [0.0, 0.0], full, full.tobytes()
+
+    def _key(self, *parts):
+        return parts + (self._trunc, str(self.device))
+
+    def _dev_params(self, dev):
+        """per-entry host parameters [2, B] -> device (only on a cache miss)"""
+        return torch.from_numpy(dev).to(self.device) if isinstance(dev, np.ndarray) else dev
 
     def _gen1(self, kind, p0, p1):
-        nb, sc, dev = self._params(p0, p1)
+        nb, sc, dev, key = self._params(p0, p1)
         D = self._trunc
-        out = self._new(nb * D * D)
-        L.call("b200_gen_gate1", kind, D, nb, sc[0], sc[1], _ptr(dev), _ptr(out), self._stream())
-        return out.view(nb, D, D)
+
+        def build():
+            out = self._new(nb * D * D)
+            L.call("b200_gen_gate1", kind, D, nb, sc[0], sc[1], _ptr(self._dev_params(dev)), _ptr(out), self._stream())
+            return out.view(nb, D, D)
+
+        return TABLES.get(None if key is None else self._key("g1", kind, key), build)
 
     def _gen_diag(self, kind, p0):
-        nb, sc, dev = self._params(p0)
+        nb, sc, dev, key = self._params(p0)
         D = self._trunc
         per = D * D if kind == L.DIAG_CROSS_KERR else D
-        out = self._new(nb * per)
-        L.call("b200_gen_diag", kind, D, nb, sc[0], _ptr(dev), _ptr(out), self._stream())
-        return out.view(nb, per)
+
+        def build():
+            out = self._new(nb * per)
+            L.call("b200_gen_diag", kind, D, nb, sc[0], _ptr(self._dev_params(dev)), _ptr(out), self._stream())
+            return out.view(nb, per)
+
+        return TABLES.get(None if key is None else self._key("gd", kind, key), build)
 
     def _gen2(self, kind, p0, p1=0.0):
-        nb, sc, dev = self._params(p0, p1)
+        nb, sc, dev, key = self._params(p0, p1)
         D = self._trunc
         P = L.packed_size(D)
-        out = self._new(nb * P)
-        L.call("b200_gen_gate2", kind, D, nb, sc[0], sc[1], _ptr(dev), _ptr(out), self._stream())
-        return out.view(nb, P)
+
+        def build():
+            out = self._new(nb * P)
+            L.call("b200_gen_gate2", kind, D, nb, sc[0], sc[1], _ptr(self._dev_params(dev)), _ptr(out), self._stream())
+            return out.view(nb, P)
+
+        return TABLES.get(None if key is None else self._key("g2", kind, key), build)
 
     def _upload_matrix(self, mat):
         mat = np.ascontiguousarray(np.asarray(mat, dtype=C128))
         D = self._trunc
         if mat.shape != (D, D):
             raise ValueError("single-mode operator must have shape (cutoff, cutoff)")
-        return torch.from_numpy(mat).to(self.device).view(1, D, D)
+        return TABLES.get(self._key("mat", mat.tobytes()),
+                          lambda: torch.from_numpy(mat).to(self.device).view(1, D, D))
 
     @staticmethod
     def _expand(t, nb):
@@ -386,7 +465,8 @@ class DeviceCircuit:
         for i in range(0, len(axes), L.MAX_AXES):
             chunk = axes[i:i + L.MAX_AXES]
             nb = max(t.shape[0] for _, _, t in chunk)
-            tabs = torch.stack([self._expand(t, nb) for _, _, t in chunk], dim=1).contiguous()
+            tabs = TABLES.get(_derived("stack", nb, *[t for _, _, t in chunk]),
+                              lambda: torch.stack([self._expand(t, nb) for _, _, t in chunk], dim=1).contiguous())
             k = len(chunk)
             strides = (C.c_int64 * k)(*[s for s, _, _ in chunk])
             conjs = (C.c_int * k)(*[c for _, c, _ in chunk])
@@ -511,16 +591,24 @@ class DeviceCircuit:
         elif pend[0] == "diag":
             d = pend[1]
             nb = max(U.shape[0], d.shape[0])
-            U = self._expand(U, nb)  # freshly generated table: folding in place is safe
-            L.call("b200_fold_diag_gate1", D, nb, _ptr(U), _ptr(self._expand(d, nb)), None, self._stream())
-            self._pending[mode] = ("dense", U)
+
+            def build():
+                out = self._expand(U, nb).clone()  # cached tables are shared: never folded in place
+                L.call("b200_fold_diag_gate1", D, nb, _ptr(out), _ptr(self._expand(d, nb)), None, self._stream())
+                return out
+
+            self._pending[mode] = ("dense", TABLES.get(_derived("fold1", U, d, 0), build))
         else:
             P = pend[1]
             nb = max(U.shape[0], P.shape[0])
-            out = self._new(nb * D * D).view(nb, D, D)
-            L.call("b200_compose_gate1", D, nb, _ptr(self._expand(U, nb)), _ptr(self._expand(P, nb)),
-                   _ptr(out), self._stream())
-            self._pending[mode] = ("dense", out)
+
+            def build():
+                out = self._new(nb * D * D).view(nb, D, D)
+                L.call("b200_compose_gate1", D, nb, _ptr(self._expand(U, nb)), _ptr(self._expand(P, nb)),
+                       _ptr(out), self._stream())
+                return out
+
+            self._pending[mode] = ("dense", TABLES.get(_derived("compose", U, P), build))
 
     def _queue_diag(self, d, mode):
         self._touch(mode)
@@ -533,16 +621,24 @@ class DeviceCircuit:
             self._pending[mode] = ("diag", d)
         elif pend[0] == "diag":
             nb = max(d.shape[0], pend[1].shape[0])
-            out = self._new(nb * D).view(nb, D)
-            L.call("b200_mul_tables", nb * D, _ptr(self._expand(d, nb)), _ptr(self._expand(pend[1], nb)), 0,
-                   _ptr(out), self._stream())
-            self._pending[mode] = ("diag", out)
+
+            def build():
+                out = self._new(nb * D).view(nb, D)
+                L.call("b200_mul_tables", nb * D, _ptr(self._expand(d, nb)), _ptr(self._expand(pend[1], nb)), 0,
+                       _ptr(out), self._stream())
+                return out
+
+            self._pending[mode] = ("diag", TABLES.get(_derived("mul", d, pend[1]), build))
         else:
             P = pend[1]
             nb = max(d.shape[0], P.shape[0])
-            P = self._expand(P, nb).clone()
-            L.call("b200_fold_diag_gate1", D, nb, _ptr(P), None, _ptr(self._expand(d, nb)), self._stream())
-            self._pending[mode] = ("dense", P)
+
+            def build():
+                out = self._expand(P, nb).clone()
+                L.call("b200_fold_diag_gate1", D, nb, _ptr(out), None, _ptr(self._expand(d, nb)), self._stream())
+                return out
+
+            self._pending[mode] = ("dense", TABLES.get(_derived("fold1", P, 0, d), build))
 
     def _activate(self, modes):
         """Lazy vacuum: bring the still-factored modes among ``modes`` into the device tensor.  Such
@@ -619,10 +715,16 @@ class DeviceCircuit:
                 self._flush([m])
         if pre[0] is not None or pre[1] is not None:
             nb = max([G.shape[0]] + [p.shape[0] for p in pre if p is not None])
-            G = self._expand(G, nb).clone()
-            p1 = self._expand(pre[0], nb) if pre[0] is not None else None
-            p2 = self._expand(pre[1], nb) if pre[1] is not None else None
-            L.call("b200_fold_diag_gate2", rule, D, nb, _ptr(G), _ptr(p1), _ptr(p2), None, None, self._stream())
+            G0 = G
+
+            def build():
+                out = self._expand(G0, nb).clone()
+                p1 = self._expand(pre[0], nb) if pre[0] is not None else None
+                p2 = self._expand(pre[1], nb) if pre[1] is not None else None
+                L.call("b200_fold_diag_gate2", rule, D, nb, _ptr(out), _ptr(p1), _ptr(p2), None, None, self._stream())
+                return out
+
+            G = TABLES.get(_derived("fold2", rule, G0, pre[0], pre[1]), build)
         self._emit_pair(G, rule, m1, m2)
 
     # ------------------------------------------------------------------ named gates (circuit.py:537-598)

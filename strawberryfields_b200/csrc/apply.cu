@@ -286,13 +286,20 @@ struct DiagAxes {
   I stride[B200_MAX_AXES];
 };
 
-// state[e] *= prod_k tabs[k][digit_k(e)] -- every pending diagonal gate in one pass
+// state[e] *= prod_k tabs[k][digit_k(e)] -- every pending diagonal gate in one pass.
+// No per-element divide: the index is split as e = row * L + i with L = D^j (<= DIAG_LOW_MAX) the
+// extent of the innermost axes.  The product over the axes inside a row (stride < L) is a table of
+// L factors built once per CTA in shared memory; the product over the outer axes is one factor per
+// row, computed once per row.  Per element: one LDS.128 and two complex multiplies, two elements per
+// thread in flight.
+constexpr int DIAG_LOW_MAX = 2048;
 template <typename I>
 __global__ void __launch_bounds__(256)
-k_apply_diag_multi(cplx* __restrict__ state, I total, int D, const DiagAxes<I> md, const cplx* __restrict__ tabs,
-                   long long state_batch_stride, long long tab_batch_stride) {
+k_apply_diag_multi(cplx* __restrict__ state, I nrows, int L, int D, const DiagAxes<I> md,
+                   const cplx* __restrict__ tabs, long long state_batch_stride, long long tab_batch_stride) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  cplx* T = reinterpret_cast<cplx*>(smem_raw);
+  cplx* T = reinterpret_cast<cplx*>(smem_raw);   // [naxes][D]
+  cplx* low = T + md.naxes * D;                  // [L]
   const int batch = blockIdx.z;
   const cplx* tg = tabs + (size_t)batch * tab_batch_stride;
   for (int i = threadIdx.x; i < md.naxes * D; i += blockDim.x) {
@@ -301,14 +308,27 @@ k_apply_diag_multi(cplx* __restrict__ state, I total, int D, const DiagAxes<I> m
     T[i] = v;
   }
   __syncthreads();
+  for (int i = threadIdx.x; i < L; i += blockDim.x) {
+    cplx f = make_double2(1.0, 0.0);
+    for (int k = 0; k < md.naxes; ++k)
+      if (md.stride[k] < (I)L) f = cmul(f, T[k * D + (i / (int)md.stride[k]) % D]);
+    low[i] = f;
+  }
+  __syncthreads();
   cplx* base = state + (size_t)batch * state_batch_stride;
-  const I nthreads = (I)gridDim.x * blockDim.x;
-  const I uD = (I)D;
-  for (I e = (I)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += nthreads) {
-    cplx v = base[e];
-    cplx f = T[(int)((e / md.stride[0]) % uD)];
-    for (int k = 1; k < md.naxes; ++k) f = cmul(f, T[k * D + (int)((e / md.stride[k]) % uD)]);
-    base[e] = cmul(v, f);
+  for (I row = blockIdx.x; row < nrows; row += gridDim.x) {
+    cplx fh = make_double2(1.0, 0.0);
+    for (int k = 0; k < md.naxes; ++k)
+      if (md.stride[k] >= (I)L) fh = cmul(fh, T[k * D + (int)((row / (md.stride[k] / (I)L)) % (I)D)]);
+    cplx* p = base + (size_t)row * L;
+    int i = threadIdx.x;
+    for (; i + (int)blockDim.x < L; i += 2 * blockDim.x) {
+      cplx v0 = p[i], v1 = p[i + blockDim.x];
+      cplx f0 = cmul(low[i], fh), f1 = cmul(low[i + blockDim.x], fh);
+      p[i] = cmul(v0, f0);
+      p[i + blockDim.x] = cmul(v1, f1);
+    }
+    if (i < L) p[i] = cmul(p[i], cmul(low[i], fh));
   }
 }
 
@@ -521,8 +541,16 @@ int b200_apply_diag_multi(b200_c128* state_dev, int64_t total, int D, int naxes,
   B200_CHECK_ARG(naxes >= 1 && naxes <= B200_MAX_AXES, "apply_diag_multi: bad axis count");
   B200_CHECK_ARG(D >= 1 && D <= B200_MAX_CUTOFF && total >= 1 && nbatch >= 1, "apply_diag_multi: bad geometry");
   for (int k = 0; k < naxes; ++k) B200_CHECK_ARG(strides[k] >= 1, "apply_diag_multi: bad stride");
-  dim3 grid(diag_blocks(total), 1, nbatch);
-  size_t smem = (size_t)naxes * D * sizeof(cplx);
+  // L = D^j: the largest power of the cutoff that divides the state and fits the row table
+  long long Lr = 1;
+  while (D > 1 && Lr * D <= DIAG_LOW_MAX && total % (Lr * D) == 0) Lr *= D;
+  for (int k = 0; k < naxes; ++k)
+    B200_CHECK_ARG(strides[k] < Lr ? Lr % (strides[k] * D) == 0 : strides[k] % Lr == 0,
+                   "apply_diag_multi: axis stride does not tile the state");
+  const long long nrows = total / Lr;
+  long long want = nrows < 148 * 8 ? nrows : 148 * 8;
+  dim3 grid((unsigned)want, 1, nbatch);
+  size_t smem = ((size_t)naxes * D + (size_t)Lr) * sizeof(cplx);
   if (total < (1ll << 32)) {
     DiagAxes<unsigned> md;
     md.naxes = naxes;
@@ -531,7 +559,8 @@ int b200_apply_diag_multi(b200_c128* state_dev, int64_t total, int D, int naxes,
       md.conj[k] = conj_flags[k];
     }
     k_apply_diag_multi<unsigned><<<grid, 256, smem, (cudaStream_t)stream>>>(
-        (cplx*)state_dev, (unsigned)total, D, md, (const cplx*)tabs_dev, state_batch_stride, tab_batch_stride);
+        (cplx*)state_dev, (unsigned)nrows, (int)Lr, D, md, (const cplx*)tabs_dev, state_batch_stride,
+        tab_batch_stride);
   } else {
     DiagAxes<unsigned long long> md;
     md.naxes = naxes;
@@ -540,7 +569,7 @@ int b200_apply_diag_multi(b200_c128* state_dev, int64_t total, int D, int naxes,
       md.conj[k] = conj_flags[k];
     }
     k_apply_diag_multi<unsigned long long><<<grid, 256, smem, (cudaStream_t)stream>>>(
-        (cplx*)state_dev, (unsigned long long)total, D, md, (const cplx*)tabs_dev, state_batch_stride,
+        (cplx*)state_dev, (unsigned long long)nrows, (int)Lr, D, md, (const cplx*)tabs_dev, state_batch_stride,
         tab_batch_stride);
   }
   return cuda_status("apply_diag_multi");
