@@ -126,7 +126,8 @@ class ClockSampler:
 
 def cpu_reference_run(n_modes, D, steps, warmup):
     """The oracle port (reference loop structure, numba selection-rule kernels) on the host:
-    one step = the config-2 circuit generator at ``n_modes`` modes."""
+    one step = the config-2 circuit generator at ``n_modes`` modes.  Only used when the installed copy of
+    the reference (oracle/_ref) is missing."""
     from oracle.fock_oracle import OracleBackend
     from strawberryfields_b200 import workloads as W
 
@@ -147,26 +148,89 @@ def cpu_reference_run(n_modes, D, steps, warmup):
     return updates / dt, dt / steps, len(calls)
 
 
+# The prefix of the config-2 call list the reference is timed on at FULL size (8 modes, cutoff 10, 1e8
+# amplitudes): one gate of every kind on the path.  The whole circuit takes the reference ~40 min
+# (25-35 s per gate, measured in the build container), BASELINE.md section 4.3 prescribes a fixed prefix.
+REF_PREFIX = ("squeeze", "displacement", "rotation", "beamsplitter")
+
+
+def reference_prefix_calls(n_modes):
+    from strawberryfields_b200 import workloads as W
+
+    calls, out = W.config2_circuit(n_modes, seed=42), []
+    for kind in REF_PREFIX:
+        out.append(next(c for c in calls if c[0] == kind))
+    return out
+
+
+def unmodified_reference_run(n_modes, D, kinds, steps):
+    """Time the UNMODIFIED reference fock backend (``strawberryfields.backends.fockbackend.FockBackend`` from
+    oracle/_ref, installed by oracle/build_ref.py; absent third-party imports stubbed by oracle/ref_shim.py)
+    on the host: ``steps`` times the gates ``kinds`` of the config-2 prefix on a full-size state.  The numba
+    kernels are compiled beforehand on a cutoff-2 state of the same rank (the JIT signature depends on the
+    rank only).  Returns (updates/s, seconds per step, gates per step) or None when the installed
+    reference is missing."""
+    try:
+        from oracle import ref_shim
+
+        if not ref_shim.available():
+            return None
+        ref_shim.install()
+        from strawberryfields.backends.fockbackend import FockBackend
+    except Exception as exc:  # pragma: no cover - reported by the caller
+        sys.stderr.write("reference arm: the installed reference is not importable (%r)\n" % (exc,))
+        return None
+    from strawberryfields_b200 import workloads as W
+
+    calls = [c for c in reference_prefix_calls(n_modes) if c[0] in kinds]
+    warm = FockBackend()
+    warm.begin_circuit(n_modes, cutoff_dim=2)
+    W.run_calls(warm, calls)
+    be = FockBackend()
+    be.begin_circuit(n_modes, cutoff_dim=D)
+    W.run_calls(be, [c for c in reference_prefix_calls(n_modes) if c[0] == "displacement"])  # leave the vacuum
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        W.run_calls(be, calls)
+    dt = time.perf_counter() - t0
+    return len(calls) * D ** n_modes * steps / dt, dt / steps, len(calls)
+
+
 def reference_arm(args):
-    """``--impl reference``: the reference algorithm's CPU port on this box's host cores."""
+    """``--impl reference``: the reference's own CPU implementation of the path on this box's host cores --
+    the unmodified reference (oracle/_ref) on a full-size gate prefix of the SAME workload (config 2: 8 modes,
+    cutoff 10); the oracle port on a reduced size only if the installed reference is missing."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_modes, D = 6, 10
-    steps, warmup = max(1, min(args.steps, 3)), min(args.warmup, 1)
-    val, per_step, ngates = cpu_reference_run(n_modes, D, steps, warmup)
-    sample = "config-2 generator at %d modes, cutoff %d (%d amplitudes, %d gates) per step" % (
-        n_modes, D, D ** n_modes, ngates)
+    n_modes, D = 8, 10
+    steps, warmup = 1, 0   # one step is ~2 minutes of host time; the JIT warm-up runs on a cutoff-2 state
+    res = unmodified_reference_run(n_modes, D, REF_PREFIX, steps)
+    if res is not None:
+        val, per_step, ngates = res
+        kind, same = "reference", True
+        sample = ("the first %s of the config-2 call list (%d gates) on the full-size state: %d modes, cutoff %d, "
+                  "%d amplitudes; %.0f s per step" % (" + ".join(REF_PREFIX), ngates, n_modes, D, D ** n_modes, per_step))
+        note = ("unmodified strawberryfields FockBackend (oracle/_ref, installed by oracle/build_ref.py; thewalrus "
+                "gate recursions bound to oracle/gates.py); single-threaded like the reference (numba kernels "
+                "without parallel=True, D x D numpy)")
+    else:
+        n_modes = 6
+        val, per_step, ngates = cpu_reference_run(n_modes, D, 1, 0)
+        kind, same = "port", False
+        sample = "config-2 generator at %d modes, cutoff %d (%d amplitudes, %d gates) per step" % (
+            n_modes, D, D ** n_modes, ngates)
+        note = "oracle/_ref missing: port = oracle/fock_oracle.py style='reference' on a reduced size"
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "complex128", "data": "synthetic",
-        "config": {"workload": "BASELINE config 2 (8-mode D=10 pure interferometer circuit); reference arm "
-                               "runs a bounded sample: " + sample},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
-                         "host_cores_available": os.cpu_count(),
-                         "note": "the reference fock backend is single-threaded (numba kernels without "
-                                 "parallel=True, D x D numpy); port = oracle/fock_oracle.py style='reference'"},
+        "config": {"workload": "BASELINE config 2: 8-mode pure state, Sgate+Dgate per mode + random rectangular "
+                               "interferometer; cutoff 10, 1e+08 stored complex128 elements; the reference arm "
+                               "times a gate prefix: " + sample,
+                   "same_config": same, "requested_steps": args.steps, "requested_warmup": args.warmup},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample,
+                         "host_cores_available": os.cpu_count(), "note": note},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -233,6 +297,157 @@ def c1_arm(args):
     print(json.dumps(line))
 
 
+
+# ------------------------------------------------------------------------------ sharded parity
+def sharded_parity(be, calls, n_modes, D, rank, world, lazy, exchange, n_probs=1000, time_steps=3):
+    """Correctness of the sharded GPU path, recorded in the bench line itself (every rank calls this).
+
+    (a) single-photon transfer: |1_k> through the passive part of the circuit (the interferometer) on
+        the SHARDED state gives <1_j|psi> = U[j, k] -- the analytic N x N mode transformation;
+    (b) the state the sharded circuit ends in is compared with an UNSHARDED run of the same circuit on
+        rank 0's GPU: trace, ``n_probs`` sampled Fock probabilities, every single-mode marginal
+        (tolerance of the north star: 1e-12 absolute);
+    (c) a seeded MeasureFock gives the same outcome, and the same post-measurement probabilities.
+    Also times the unsharded circuit on rank 0 (the same-workload single-GPU reference of the strong
+    scaling figure).  Returns (parity dict, single-GPU ms per step or None)."""
+    import torch
+    import torch.distributed as dist
+
+    from strawberryfields_b200 import B200FockBackend
+    from strawberryfields_b200 import workloads as W
+
+    # (a) ------------------------------------------------------------------------------------------
+    passive = [c for c in calls if c[0] in ("rotation", "beamsplitter")]
+    U = W.interferometer_unitary(n_modes, passive)
+    k = n_modes // 2
+    be.reset()
+    be.prepare_fock_state(1, k)
+    W.run_calls(be, passive)
+    sp_err = 0.0
+    for j in range(n_modes):
+        o = [0] * n_modes
+        o[j] = 1
+        sp_err = max(sp_err, abs(complex(be.circuit.element(o)[0]) - U[j, k]))
+    sp_norm = abs(be.state().trace() - 1.0)
+
+    # (b) ------------------------------------------------------------------------------------------
+    rng = np.random.RandomState(123)
+    outcomes = [[0] * n_modes]
+    while len(outcomes) < n_probs:  # low photon numbers: where the probability mass is
+        o = rng.choice(3, size=n_modes, p=[0.7, 0.2, 0.1])
+        outcomes.append([int(x) for x in o])
+    be.reset()
+    W.run_calls(be, calls)
+    st = be.state()
+    got = {"trace": st.trace(), "probs": np.array([st.fock_prob(o) for o in outcomes]),
+           "marg": np.array([np.real(np.diag(st.reduced_dm([m]))) for m in range(n_modes)])}
+    np.random.seed(7)
+    got["outcome"] = be.measure_fock([0, n_modes - 1])
+    st2 = be.state()
+    got["post"] = np.array([st2.fock_prob(o) for o in outcomes[:64]])
+
+    res = torch.zeros(8, dtype=torch.float64, device=DEVICE)
+    if rank == 0:
+        ref = B200FockBackend()
+        ref.begin_circuit(n_modes, cutoff_dim=D)
+        W.run_calls(ref, calls)
+        ref.circuit._flush()
+        torch.cuda.synchronize() if DEVICE == "cuda" else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(time_steps):   # steady state, like the timed region of the sharded arm
+            W.run_calls(ref, calls)
+            ref.circuit._flush()
+        e1.record()
+        torch.cuda.synchronize() if DEVICE == "cuda" else None
+        single_ms = e0.elapsed_time(e1) / time_steps
+        ref.reset()
+        W.run_calls(ref, calls)
+        rst = ref.state()
+        want_probs = np.array([rst.fock_prob(o) for o in outcomes])
+        want_marg = np.array([np.real(np.diag(rst.reduced_dm([m]))) for m in range(n_modes)])
+        np.random.seed(7)
+        want_out = ref.measure_fock([0, n_modes - 1])
+        rst2 = ref.state()
+        want_post = np.array([rst2.fock_prob(o) for o in outcomes[:64]])
+        res[0] = abs(got["trace"] - rst.trace())
+        res[1] = np.abs(got["probs"] - want_probs).max()
+        res[2] = np.abs(got["marg"] - want_marg).max()
+        res[3] = 1.0 if np.array_equal(got["outcome"], want_out) else 0.0
+        res[4] = np.abs(got["post"] - want_post).max()
+        res[5] = single_ms
+        res[6] = float(np.sum(want_probs))
+        del ref, rst, rst2
+        if DEVICE == "cuda":
+            torch.cuda.empty_cache()
+    if world > 1:
+        dist.broadcast(res, src=0)
+    r = res.cpu().numpy()
+    parity = {
+        "max_abs_err": float(max(sp_err, r[0], r[1], r[2], r[4])),
+        "tolerance": 1e-12,
+        "single_photon_transfer_max_abs_err": float(sp_err), "single_photon_norm_err": float(sp_norm),
+        "vs_unsharded_run_on_rank0": {"trace_abs_err": float(r[0]), "fock_probs_compared": len(outcomes),
+                                      "fock_prob_max_abs_err": float(r[1]), "probability_mass_compared": float(r[6]),
+                                      "single_mode_marginals_max_abs_err": float(r[2]),
+                                      "post_measurement_prob_max_abs_err": float(r[4])},
+        "measure_equal": bool(r[3] == 1.0), "measure_seed": 7, "measured_modes": [0, n_modes - 1],
+        "measure_outcome": [int(x) for x in np.asarray(got["outcome"]).reshape(-1)],
+    }
+    return parity, float(r[5])
+
+
+def ten_mode_block(world, rank, D, exchange, steps=3):
+    """BASELINE config 5, second half: the 10-mode cutoff-10 pure state (1e10 amplitudes, 160 GB) sharded
+    over 8 GPUs -- ms per circuit, exchanges, and the single-photon transfer check on the sharded state
+    (the reference cannot hold 160 GB)."""
+    import torch
+    import torch.distributed as dist
+
+    from strawberryfields_b200 import B200FockBackend
+    from strawberryfields_b200 import workloads as W
+
+    n = 10
+    calls = W.config2_circuit(n, seed=42)
+    be = B200FockBackend()
+    be.begin_circuit(n, cutoff_dim=D, shard=True, exchange=exchange)
+    W.run_calls(be, calls)
+    be.circuit._flush()
+    dist.barrier()
+    torch.cuda.synchronize()
+    x0 = be.circuit.exchanges
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        W.run_calls(be, calls)
+        be.circuit._flush()
+    e1.record()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=DEVICE)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ex = (be.circuit.exchanges - x0) / steps
+    passive = [c for c in calls if c[0] in ("rotation", "beamsplitter")]
+    U = W.interferometer_unitary(n, passive)
+    be.reset()
+    be.prepare_fock_state(1, 4)
+    W.run_calls(be, passive)
+    err = 0.0
+    for j in range(n):
+        o = [0] * n
+        o[j] = 1
+        err = max(err, abs(complex(be.circuit.element(o)[0]) - U[j, 4]))
+    norm_err = abs(be.state().trace() - 1.0)
+    be.circuit._bufs = be.circuit._buf = be.circuit._backing = be.circuit._peers = None
+    del be
+    torch.cuda.empty_cache()
+    t = float(ms.item())
+    return {"modes": n, "amplitudes": 10 ** n, "state_GB": 16 * 10 ** n / 1e9, "gates": len(calls), "steps": steps,
+            "ms_per_step": t, "updates_per_s": len(calls) * 10 ** n / (t * 1e-3), "exchanges_per_step": ex,
+            "parity": {"single_photon_transfer_max_abs_err": float(err), "norm_err": float(norm_err),
+                       "tolerance": 1e-12}}
+
+
 # ------------------------------------------------------------------------------ b200 arm
 def b200_arm(args):
     import torch
@@ -289,8 +504,7 @@ def b200_arm(args):
     # lazy-vacuum option (modes stay product factors until a two-mode gate needs them).
     # Default: the gates are applied to whatever state the previous step left (a generic dense state),
     # i.e. the steady-state cost of the kernels alone.
-    if args.from_vacuum:
-        shard_kw = dict(shard_kw, lazy_vacuum=True)
+    value_kw = dict(shard_kw, lazy_vacuum=bool(args.from_vacuum))
 
     def one_step(b):
         if args.from_vacuum:
@@ -299,7 +513,7 @@ def b200_arm(args):
         b.circuit._flush()
 
     be = B200FockBackend()
-    be.begin_circuit(n_modes, cutoff_dim=D, fuse=fuse, **shard_kw)
+    be.begin_circuit(n_modes, cutoff_dim=D, fuse=fuse, **value_kw)
     for _ in range(args.warmup):
         one_step(be)
     sampler = ClockSampler(local_rank)
@@ -380,6 +594,8 @@ def b200_arm(args):
             o[m] = k
             outcomes.append(o)
 
+    # the plugin with its default options: every step is a whole program run from vacuum (lazy vacuum, gate
+    # calls deferred until state() is asked for -- DESIGN 4.7)
     be2 = B200FockBackend()
     be2.begin_circuit(n_modes, cutoff_dim=D, fuse=fuse, **shard_kw)
 
@@ -408,16 +624,35 @@ def b200_arm(args):
     e2e_value = updates_per_step * args.steps / (float(ms2.item()) * 1e-3)
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(ptab.nbytes),
            "d2h_bytes_per_step": int(8 * (len(outcomes) + 1) * nb),
-           "api": "B200FockBackend.begin_circuit/gates/state().trace()/fock_prob()"}
+           "api": "B200FockBackend.begin_circuit/gates/state().trace()/fock_prob()",
+           "state_at_step_start": "vacuum (backend.reset() every step, plugin defaults: lazy vacuum)"}
 
-    # ---- CPU baseline (rank 0, N = 1 only) -----------------------------------------------------
+    # ---- sharded arm: parity of the sharded GPU path + the same workload on ONE GPU -------------
+    parity = single_ms = ten = None
+    if sharded and args.workload == "c2" and not args.no_parity:
+        parity, single_ms = sharded_parity(be2, calls, n_modes, D, rank, world, args.from_vacuum, args.exchange,
+                                            n_probs=args.parity_probs)
+        if world == 8 and n_modes == 9 and not args.no_ten_mode:
+            be.circuit._bufs = be.circuit._buf = be.circuit._backing = be.circuit._peers = None
+            be2.circuit._bufs = be2.circuit._buf = be2.circuit._backing = be2.circuit._peers = None
+            torch.cuda.empty_cache()
+            ten = ten_mode_block(world, rank, D, args.exchange)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, per_step, ngates = cpu_reference_run(6, 10, 1, 0)
-        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": "config-2 generator at 6 modes, cutoff 10 (1e6 amplitudes, %d gates), 1 step = %.1f s"
-                         % (ngates, per_step),
-               "host_cores_available": os.cpu_count()}
+        res = unmodified_reference_run(8, 10, ("beamsplitter",), 1) if args.workload == "c2" else None
+        if res is not None:
+            v, per_step, ngates = res
+            cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "reference",
+                   "sample": "one BSgate of the config-2 circuit on the full-size state (8 modes, cutoff 10, 1e8 "
+                             "amplitudes) with the unmodified reference FockBackend (oracle/_ref): %.1f s" % per_step,
+                   "host_cores_available": os.cpu_count()}
+        else:
+            v, per_step, ngates = cpu_reference_run(6, 10, 1, 0)
+            cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": "config-2 generator at 6 modes, cutoff 10 (1e6 amplitudes, %d gates), 1 step = %.1f s"
+                             % (ngates, per_step),
+                   "host_cores_available": os.cpu_count()}
 
     if rank == 0:
         line = {
@@ -462,6 +697,12 @@ def b200_arm(args):
                 if sel:
                     line["exchange"][part] = {"ms": sum(t for _, t in sel) / len(sel) * 1e3,
                                               "GBps": sum(nb for nb, _ in sel) / sum(t for _, t in sel) / 1e9}
+        if parity is not None:
+            line["parity"] = parity
+            line["single_gpu_same_workload_ms"] = single_ms
+            line["strong_efficiency"] = single_ms / (world * ms_total / args.steps)
+        if ten is not None:
+            line["ten_mode"] = ten
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))
@@ -487,6 +728,9 @@ def main():
     ap.add_argument("--fuse", default="fold", choices=["tile", "fold", "off"],
                     help="gate queue: diagonal / same-mode folding (default), + multi-gate tile passes, "
                          "or one pass per gate")
+    ap.add_argument("--no-parity", action="store_true", help="sharded arm: skip the parity block")
+    ap.add_argument("--parity-probs", type=int, default=1000, help="sharded arm: Fock probabilities compared")
+    ap.add_argument("--no-ten-mode", action="store_true", help="8-GPU sharded arm: skip the 10-mode / 160 GB block")
     ap.add_argument("--from-vacuum", action="store_true",
                     help="every step resets to vacuum first and uses the lazy-vacuum option (not yet the default: "
                          "unmeasured in round 1)")

@@ -37,7 +37,10 @@ typedef struct { double re, im; } b200_c128;
 #define B200_EINVAL (-1)       /* bad argument */
 #define B200_EUNSUPPORTED (-2) /* cutoff / rank outside the compiled range */
 
-#define B200_MAX_CUTOFF 64        /* largest cutoff any kernel accepts */
+#define B200_MAX_CUTOFF 64        /* largest cutoff any kernel accepts (one-mode, diagonal, reductions) */
+#define B200_MAX_PAIR_CUTOFF 27   /* two-axis operators: the packed table (b200_packed_size) must fit the
+                                     227 KB of shared memory the gate kernels stage it in; b200_gen_gate2
+                                     additionally generates BS / MZ / S2 tables up to cutoff 32 only */
 #define B200_MAX_FAST_CUTOFF 16   /* cutoffs <= this use the register-blocked kernels */
 #define B200_MAX_AXES 24          /* rank limit of the strided gather/reduce kernel */
 
@@ -197,6 +200,44 @@ int b200_norm2(const b200_c128* psi_dev, int64_t n, double* out_dev, double* par
 /* state *= (re, im) / (*divisor_dev if divisor_dev else 1)   [sqrt_div: divide by sqrt] */
 int b200_scale(b200_c128* dev, int64_t n, double re, double im, const double* divisor_dev,
                int sqrt_div, void* stream);
+
+/* ---- multi-GPU axis exchange (the reference has no distributed path) ------------
+ * One launch performs a rank's whole share of the all-to-all that swaps the sharded leading
+ * axes of the state with local ones.  For every source s the copy is
+ *   dst[s][dst_base[s] + sum_j i_j*ds[j] + r] = src[s][src_base[s] + sum_j i_j*ss[j] + r],
+ * 0 <= i_j < ext[j], 0 <= r < run (elements, contiguous on both sides).  src[] / dst[] may be
+ * peer-device pointers (CUDA IPC + peer access): "pull" passes the peers' old shards as src,
+ * "push" the peers' new shards as dst.  The payload moves through shared memory with the bulk
+ * copy engine (cp.async.bulk global->shared->global), sources interleaved starting at
+ * `first_src`.  local_src >= 0 (then == first_src): that source and its destination are both
+ * local; its block is copied with plain loads / stores by the CTAs the link does not need
+ * (-1: every source goes through the bulk path).  bulk_ctas: CTAs driving the bulk path,
+ * 0 = default (48 next to a local block, else one per SM).                                       */
+#define B200_XCHG_MAX_AXES 12
+#define B200_XCHG_MAX_PEERS 32
+typedef struct {
+  int n_axes;
+  int n_src;
+  int first_src;
+  int32_t ext[B200_XCHG_MAX_AXES];
+  int64_t ss[B200_XCHG_MAX_AXES], ds[B200_XCHG_MAX_AXES];
+  int64_t run;
+  const void* src[B200_XCHG_MAX_PEERS];
+  void* dst[B200_XCHG_MAX_PEERS];
+  int64_t src_base[B200_XCHG_MAX_PEERS], dst_base[B200_XCHG_MAX_PEERS];
+} b200_xchg_desc;
+int b200_exchange_copy(const b200_xchg_desc* desc, int local_src, int bulk_ctas, void* stream);
+
+/* Device-side barrier between the ranks of a sharded state, stream-ordered (no host
+ * synchronisation): flags[r] points at rank r's array of n_ranks uint64 counters (peer-mapped,
+ * zero-initialised); every rank calls with the same, strictly increasing `epoch`.  A rank that
+ * waits longer than timeout_s traps (the launch fails) instead of hanging the GPU.             */
+typedef struct {
+  int n_ranks;
+  int rank;
+  void* flags[B200_XCHG_MAX_PEERS];
+} b200_peer_flags;
+int b200_peer_barrier(const b200_peer_flags* pf, uint64_t epoch, double timeout_s, void* stream);
 
 #ifdef __cplusplus
 }

@@ -10,9 +10,11 @@ recursions in :mod:`oracle.gates`.  After that ``import strawberryfields`` works
 and ``sf.Engine("fock")`` / ``FockBackend`` / ``Circuit`` run the reference's own
 code, unmodified, from where it lies.
 
-This only works where ``/root/reference`` exists (the build container).  It is
-used by ``oracle/make_golden.py`` to write the fixtures in ``tests/golden`` and
-by the container-only differential tests; nothing on the GPU box imports it.
+In the build container the package is imported from ``/root/reference``; on the GPU box from
+``oracle/_ref``, the copy installed by ``oracle/build_ref.py``.  It is used by
+``oracle/make_golden.py`` to write the fixtures in ``tests/golden``, by the container-only
+differential tests, and by the reference arm of ``bench.py`` (``--impl reference``), which times the
+reference's own fock backend on the host cores.
 """
 from __future__ import annotations
 
@@ -21,7 +23,12 @@ import sys
 import types
 from unittest import mock
 
-REFERENCE_ROOT = os.environ.get("SF_REFERENCE_ROOT", "/root/reference")
+# where the unmodified reference package lies: the read-only tree of the build container, else the copy
+# installed by oracle/build_ref.py (oracle/_ref: git-ignored, travels to the GPU box with the snapshot)
+_INSTALLED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+REFERENCE_ROOT = os.environ.get(
+    "SF_REFERENCE_ROOT",
+    "/root/reference" if os.path.isdir("/root/reference/strawberryfields") else _INSTALLED)
 
 _STUBS = [
     "thewalrus",

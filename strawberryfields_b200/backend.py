@@ -14,7 +14,7 @@ Extra ``begin_circuit`` options: ``batch_size`` (leading batch axis, TF-backend
 semantics -- the reference fock backend ignores it), ``strict_purity`` (follow
 the reference's switch to a mixed representation on single-mode preparations),
 ``fuse`` (lazy gate queue: ``True``/``"fold"`` default, ``"tile"``, ``False``), ``lazy_vacuum``
-(untouched modes stay product factors; off by default), ``device``, and for several
+(untouched modes stay product factors and gate calls are deferred until the state is observed; on by default, ``False`` applies every gate to a dense tensor as it arrives), ``device``, and for several
 GPUs ``shard`` (``True`` or a ``torch.distributed`` group: one state over all ranks, kets and
 density matrices) with ``exchange`` (``"auto"`` | ``"p2p"`` | ``"push"`` | ``"nccl"``).
 """
@@ -146,8 +146,9 @@ class B200FockBackend(_Base):
             "strict_purity": bool(kwargs.get("strict_purity", False)),
             "fuse": kwargs.get("fuse", True),  # True|"fold": gate folding; "tile": + multi-gate tile passes; False: off
             "device": kwargs.get("device", None),
-            # keep modes that no two-mode gate has touched yet as product factors; off by default
-            "lazy_vacuum": bool(kwargs.get("lazy_vacuum", False)),
+            # keep modes that no two-mode gate has touched yet as product factors.  On by default
+            # since round 2 (measured on B200: config 2 from vacuum 13.8 ms instead of 22.8 ms, same results)
+            "lazy_vacuum": bool(kwargs.get("lazy_vacuum", True)),
         }
         self._init_modes = num_subsystems
         shard = kwargs.get("shard", False)

@@ -142,6 +142,9 @@ class DeviceCircuit:
         self._B = int(batch_size) if batch_size is not None else 1
         if self._B < 1:
             raise ValueError("batch_size must be a positive integer")
+        if self._B > L.MAX_BATCH:
+            # the kernels map the batch axis to gridDim.z
+            raise ValueError("b200fock supports batch_size <= {}".format(L.MAX_BATCH))
         self._strict = bool(strict_purity)
         # True / "fold": fold diagonal and same-mode gates, one streaming pass per remaining gate (default);
         # "tile": additionally group gates into multi-gate tile passes (scheduler.py); False: one pass per gate
@@ -275,8 +278,10 @@ class DeviceCircuit:
 
     def _vacuum(self, buf, per):
         L.call("b200_fill_zero", _ptr(buf), buf.numel(), self._stream())
-        for b in range(self._B):
-            L.call("b200_set_element", _ptr(buf), b * per, 1.0, 0.0, self._stream())
+        if self._B == 1:
+            L.call("b200_set_element", _ptr(buf), 0, 1.0, 0.0, self._stream())
+        else:
+            buf[::per] = 1.0  # one strided fill for the whole batch (torch: plumbing, not a hot path)
 
     # ------------------------------------------------------------------ reset (circuit.py:89-116)
     def reset(self, pure=None, cutoff_dim=None, num_subsystems=None):
@@ -300,12 +305,17 @@ class DeviceCircuit:
         self._pending = {}
         self._opq = []
         self._untouched = set(range(self._num_modes))
+        self._defer_log = None
+        self._inner_hint = None
         if self._lazy_opt and self._fuse == "fold" and self._num_modes > 0:
             # nothing is entangled yet: the device tensor has no axes (one amplitude, 1, per batch entry)
             self._phys = []
             self._pos = [None] * self._axes()
             self._inactive = set(range(self._num_modes))
             self._buf = torch.ones(self._B, dtype=torch.complex128, device=self.device)
+            # gate calls are only recorded until the state is first observed: the replay then knows the
+            # whole program and can choose the tensor layout (_replay)
+            self._defer_log = []
             return
         self._set_identity_layout()
         per = self._size()
@@ -368,6 +378,12 @@ class DeviceCircuit:
     def _gen2(self, kind, p0, p1=0.0):
         nb, sc, dev, key = self._params(p0, p1)
         D = self._trunc
+        if D > L.MAX_PAIR_CUTOFF:
+            # the block-packed table of a two-axis operator (D^2 + (D-1)D(2D-1)/3 entries) is staged whole in
+            # shared memory by the gate kernels: 227 KB hold it up to cutoff 27
+            raise ValueError("b200fock supports two-mode gates and the loss channel up to cutoff_dim = {} "
+                             "(single-mode and diagonal gates up to {}); got {}".format(
+                                 L.MAX_PAIR_CUTOFF, L.MAX_CUTOFF, D))
         P = L.packed_size(D)
 
         def build():
@@ -574,6 +590,38 @@ class DeviceCircuit:
                    stride1, tops, len(p.ops), perm, _ptr(coef), off, B, self._size(), off if nb > 1 else 0,
                    self._stream())
 
+    # ------------------------------------------------------------------ deferred program (lazy vacuum)
+    _PAIR_GATES = ("beamsplitter", "mzgate", "two_mode_squeeze", "cross_kerr_interaction")
+
+    def _defer(self, name, *args):
+        """Lazy vacuum: while the state of a fresh circuit has not been observed, a gate call is only
+        recorded (the engine delivers gates one call at a time, engine.py:427-444; the reference applies
+        each immediately).  Returns True when the call was recorded."""
+        log = self.__dict__.get("_defer_log")
+        if log is None:
+            return False
+        log.append((name, tuple(a.copy() if isinstance(a, np.ndarray) else a for a in args)))
+        return True
+
+    def _replay(self):
+        """Run the recorded program.  Knowing all of it, the mode that takes part in the FEWEST two-mode
+        gates is made the innermost tensor axis (it is activated first): gates on the innermost axis are the
+        slow passes (staged through shared memory), every other axis streams at the HBM rate."""
+        log = self.__dict__.get("_defer_log")
+        if log is None:
+            return
+        self._defer_log = None
+        count, first = {}, {}
+        for i, (name, args) in enumerate(log):
+            if name in self._PAIR_GATES:
+                for m in args[-2:]:
+                    count[m] = count.get(m, 0) + 1
+                    first.setdefault(m, i)
+        if count:
+            self._inner_hint = min(count, key=lambda m: (count[m], first[m]))
+        for name, args in log:
+            getattr(self, name)(*args)
+
     # ------------------------------------------------------------------ lazy queue
     def _touch(self, *modes):
         for m in modes:
@@ -647,6 +695,9 @@ class DeviceCircuit:
         new tensor once -- instead of a read + write pass over the full-size state per such gate.
         Mixed states: the factor is the rank-one matrix P|0><0|P^dagger on the (ket, bra) axes."""
         D, B = self._trunc, self._B
+        hint = self.__dict__.get("_inner_hint")
+        if not self._phys and hint is not None and hint in self._inactive:
+            modes = [hint] + [m for m in modes if m != hint]  # first activated = innermost axis
         for m in modes:
             if m not in self._inactive:
                 continue
@@ -680,6 +731,7 @@ class DeviceCircuit:
         """Move the pending single-mode operators of ``modes`` (default: all) out of the fold
         stage.  A full flush (``modes is None``) also runs every queued tile pass, after which
         the device buffer holds the up-to-date state."""
+        self._replay()
         if self._inactive:
             # descending: every activation adds the outermost axis, so a fresh vacuum ends up canonical
             self._activate(sorted(self._inactive if modes is None else modes, reverse=True))
@@ -729,15 +781,23 @@ class DeviceCircuit:
 
     # ------------------------------------------------------------------ named gates (circuit.py:537-598)
     def phase_shift(self, theta, mode):
+        if self._defer('phase_shift', theta, mode):
+            return
         self._queue_diag(self._gen_diag(L.DIAG_ROTATION, theta), mode)
 
     def kerr_interaction(self, kappa, mode):
+        if self._defer('kerr_interaction', kappa, mode):
+            return
         self._queue_diag(self._gen_diag(L.DIAG_KERR, kappa), mode)
 
     def displacement(self, r, phi, mode):
+        if self._defer('displacement', r, phi, mode):
+            return
         self._queue_dense(self._gen1(L.GATE_DISPLACEMENT, r, phi), mode)
 
     def squeeze(self, r, theta, mode):
+        if self._defer('squeeze', r, theta, mode):
+            return
         self._queue_dense(self._gen1(L.GATE_SQUEEZE, r, theta), mode)
 
     def cubic_phase_shift(self, gamma, mode):
@@ -745,6 +805,8 @@ class DeviceCircuit:
         matrix; it is applied with the generic dense kernel."""
         from scipy.linalg import expm
 
+        if self._defer("cubic_phase_shift", gamma, mode):
+            return
         D = self._trunc
         a = np.diag(np.sqrt(np.arange(1, D)), 1).astype(C128)
         x = (a + a.conj().T) * np.sqrt(self._hbar / 2)
@@ -752,19 +814,29 @@ class DeviceCircuit:
 
     def apply_matrix(self, mat, mode):
         """Arbitrary single-mode operator (host matrix [out, in])."""
+        if self._defer("apply_matrix", np.array(mat, dtype=C128), mode):
+            return
         self._queue_dense(self._upload_matrix(mat), mode)
 
     def beamsplitter(self, theta, phi, mode1, mode2):
+        if self._defer('beamsplitter', theta, phi, mode1, mode2):
+            return
         self._pair_gate(self._gen2(L.GATE_BEAMSPLITTER, theta, phi), L.RULE_SUM, mode1, mode2)
 
     def mzgate(self, phi_in, phi_ex, mode1, mode2):
+        if self._defer('mzgate', phi_in, phi_ex, mode1, mode2):
+            return
         self._pair_gate(self._gen2(L.GATE_MZ, phi_in, phi_ex), L.RULE_SUM, mode1, mode2)
 
     def two_mode_squeeze(self, r, theta, mode1, mode2):
+        if self._defer('two_mode_squeeze', r, theta, mode1, mode2):
+            return
         self._pair_gate(self._gen2(L.GATE_S2, r, theta), L.RULE_DIFF, mode1, mode2)
 
     def cross_kerr_interaction(self, kappa, mode1, mode2):
         # diagonal in both modes: commutes with pending diagonals, not with pending dense gates
+        if self._defer("cross_kerr_interaction", kappa, mode1, mode2):
+            return
         self._touch(mode1, mode2)
         if self._inactive:
             self._activate(sorted((mode1, mode2), reverse=True))
@@ -779,6 +851,8 @@ class DeviceCircuit:
 
     # ------------------------------------------------------------------ channels (circuit.py:65-87, 617-621)
     def loss(self, T, mode):
+        if self._defer("loss", T, mode):
+            return
         self._flush([mode])  # operators pending on other modes commute with this channel
         self._touch(mode)
         self._to_mixed()
@@ -864,10 +938,12 @@ class DeviceCircuit:
             self._flush()
         B, per = self._B, self._size()
         out = torch.zeros(B, dtype=torch.float64, device=self.device)
-        if self._pure:
-            for b in range(B):
-                L.call("b200_norm2", C.c_void_p(self._buf.data_ptr() + 16 * b * per), per,
-                       C.c_void_p(out.data_ptr() + 8 * b), _ptr(self._norm_part), self._stream())
+        if self._pure and B == 1:
+            L.call("b200_norm2", _ptr(self._buf), per, _ptr(out), _ptr(self._norm_part), self._stream())
+        elif self._pure:
+            # all B squared norms in one reduction: out[b] = sum_r psi[b, r] * conj(psi[b, r])
+            self._gather(self._buf, self._buf, out, [(B, per, per, 1)], [(per, 1, 1)],
+                         flags=L.FLAG_CONJ_B | L.FLAG_REAL_OUT)
         else:
             n, D = self._num_modes, self._trunc
             red = [(D, self._stride(2 * i) + self._stride(2 * i + 1), 0) for i in range(n)
@@ -935,6 +1011,7 @@ class DeviceCircuit:
         modes = list(modes)
         if self._batched:
             raise NotImplementedError("state preparation on a batched b200fock circuit is not supported yet")
+        self._replay()
         D, n, k = self._trunc, self._num_modes, len(modes)
         if (k == 1 and modes[0] in self._inactive and (not self._strict or not self._pure) and n > 1
                 and np.shape(state) == (D,)):

@@ -21,54 +21,11 @@
 // Replaces Circuit.apply_gate_BLAS (fockbackend/circuit.py:118-217),
 // Circuit.apply_twomode_gate + numba kernels (circuit.py:219-365) and, for the loss
 // channel, Circuit._apply_channel (circuit.py:65-87) of the reference.
-#include "blocks.cuh"
+#include "tasks.cuh"
 
 namespace b200 {
 
-struct Geometry {
-  // slice s (0 <= s < n_slices) -> element offset
-  //   (s / (mid*inner)) * outer_step + ((s / inner) % mid) * mid_step + (s % inner)
-  unsigned n_slices;
-  unsigned inner, mid;
-  long long outer_step, mid_step;
-  long long stride1, stride2;  // element strides of the gate axes (stride2 = 0 for SINGLE)
-  long long state_batch_stride;
-  long long coef_batch_stride;
-  int coef_count;  // packed entries to stage in shared memory
-  int conj;
-};
-
 constexpr int APPLY_THREADS = 256;
-
-// one task = two blocks of C0 + C1 = D amplitudes (C1 = 0: a single block)
-template <int C0, int C1>
-__device__ __forceinline__ void task_apply(cplx* __restrict__ p0, cplx* __restrict__ p1, long long step,
-                                           const cplx* __restrict__ M0, const cplx* __restrict__ M1) {
-  cplx x0[C0];
-  cplx x1[C1 > 0 ? C1 : 1];
-#pragma unroll
-  for (int j = 0; j < C0; ++j) x0[j] = p0[j * step];
-#pragma unroll
-  for (int j = 0; j < C1; ++j) x1[j] = p1[j * step];
-  rows_apply<C0>(p0, step, M0, x0);
-  if constexpr (C1 > 0) rows_apply<C1>(p1, step, M1, x1);
-}
-
-template <int D>
-__device__ __forceinline__ void task_dispatch(int c0, cplx* p0, cplx* p1, long long step, const cplx* M0,
-                                              const cplx* M1) {
-#define B200_CASE(N) \
-  case N:            \
-    if constexpr (N <= D) task_apply<N, D - N>(p0, p1, step, M0, M1); \
-    break;
-  switch (c0) {
-    B200_CASE(1) B200_CASE(2) B200_CASE(3) B200_CASE(4) B200_CASE(5) B200_CASE(6) B200_CASE(7) B200_CASE(8)
-    B200_CASE(9) B200_CASE(10) B200_CASE(11) B200_CASE(12) B200_CASE(13) B200_CASE(14) B200_CASE(15)
-    B200_CASE(16)
-    default: break;
-  }
-#undef B200_CASE
-}
 
 __device__ __forceinline__ void stage_coef(cplx* M, const cplx* cg, int n, int conj) {
   for (int i = threadIdx.x; i < n; i += APPLY_THREADS) {
@@ -287,15 +244,16 @@ struct DiagAxes {
 };
 
 // state[e] *= prod_k tabs[k][digit_k(e)] -- every pending diagonal gate in one pass.
-// No per-element divide: the index is split as e = row * L + i with L = D^j (<= DIAG_LOW_MAX) the
-// extent of the innermost axes.  The product over the axes inside a row (stride < L) is a table of
-// L factors built once per CTA in shared memory; the product over the outer axes is one factor per
-// row, computed once per row.  Per element: one LDS.128 and two complex multiplies, two elements per
-// thread in flight.
-constexpr int DIAG_LOW_MAX = 2048;
+// No per-element divide: the index is split as e = (sr * SUP + d) * L + i with L = D^j (<= DIAG_LOW_MAX)
+// the extent of the innermost axes and SUP = D rows per super-row.  The product over the axes inside a
+// row (stride < L) is a table of L factors built once per CTA in shared memory; the axis of stride L (if it
+// has a gate) contributes tab[d]; the product over the outer axes is one factor per super-row (the only
+// integer divides, amortised over SUP * L elements).  Per element: one LDS.128 and two complex multiplies,
+// four elements per thread in flight.
+constexpr int DIAG_LOW_MAX = 1024;
 template <typename I>
 __global__ void __launch_bounds__(256)
-k_apply_diag_multi(cplx* __restrict__ state, I nrows, int L, int D, const DiagAxes<I> md,
+k_apply_diag_multi(cplx* __restrict__ state, I nsuper, int SUP, int L, int D, int axisL, const DiagAxes<I> md,
                    const cplx* __restrict__ tabs, long long state_batch_stride, long long tab_batch_stride) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cplx* T = reinterpret_cast<cplx*>(smem_raw);   // [naxes][D]
@@ -316,19 +274,24 @@ k_apply_diag_multi(cplx* __restrict__ state, I nrows, int L, int D, const DiagAx
   }
   __syncthreads();
   cplx* base = state + (size_t)batch * state_batch_stride;
-  for (I row = blockIdx.x; row < nrows; row += gridDim.x) {
-    cplx fh = make_double2(1.0, 0.0);
+  const I hiL = (I)L * (I)SUP;
+  for (I sr = blockIdx.x; sr < nsuper; sr += gridDim.x) {
+    cplx fhh = make_double2(1.0, 0.0);
     for (int k = 0; k < md.naxes; ++k)
-      if (md.stride[k] >= (I)L) fh = cmul(fh, T[k * D + (int)((row / (md.stride[k] / (I)L)) % (I)D)]);
-    cplx* p = base + (size_t)row * L;
-    int i = threadIdx.x;
-    for (; i + (int)blockDim.x < L; i += 2 * blockDim.x) {
-      cplx v0 = p[i], v1 = p[i + blockDim.x];
-      cplx f0 = cmul(low[i], fh), f1 = cmul(low[i + blockDim.x], fh);
-      p[i] = cmul(v0, f0);
-      p[i + blockDim.x] = cmul(v1, f1);
+      if (md.stride[k] >= hiL) fhh = cmul(fhh, T[k * D + (int)((sr / (md.stride[k] / hiL)) % (I)D)]);
+    for (int d = 0; d < SUP; ++d) {
+      const cplx fh = axisL >= 0 ? cmul(fhh, T[axisL * D + d]) : fhh;
+      cplx* p = base + ((size_t)sr * SUP + d) * L;
+      for (int i0 = threadIdx.x; i0 < L; i0 += 4 * 256) {
+        cplx v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (i0 + u * 256 < L) v[u] = p[i0 + u * 256];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (i0 + u * 256 < L) p[i0 + u * 256] = cmul(v[u], cmul(low[i0 + u * 256], fh));
+      }
     }
-    if (i < L) p[i] = cmul(p[i], cmul(low[i], fh));
   }
 }
 
@@ -412,6 +375,16 @@ static cudaError_t launch_inner_d(cplx* state, const cplx* coef, const Geometry&
 
 static int launch_blocks(int D, cplx* state, const cplx* coef, Geometry& g, const TaskTable& tt, int nbatch,
                          cudaStream_t st) {
+  // a gate axis is the innermost one: TMA-staged persistent kernel (inner.cu); B200_INNER_LEGACY=1 keeps the
+  // round-1 kernels (cp.async staging for pair gates, register streaming for one-mode gates)
+  static const bool legacy_inner = [] {
+    const char* v = getenv("B200_INNER_LEGACY");
+    return v && v[0] == '1';
+  }();
+  if (g.inner == 1 && !legacy_inner) {
+    int status = 0;
+    if (launch_inner_tma(D, state, coef, g, tt, nbatch, st, &status)) return status;
+  }
   if (g.inner == 1 && g.stride2 != 0 && D >= 2 && D <= B200_MAX_FAST_CUTOFF) {
     // a PAIR gate with one axis innermost: staged kernel (measured 3.97 vs 2.97 TB/s streaming at D = 10;
     // the one-mode gate on the innermost axis stays on the streaming kernel: 4.6 vs 3.4 TB/s staged)
@@ -541,14 +514,20 @@ int b200_apply_diag_multi(b200_c128* state_dev, int64_t total, int D, int naxes,
   B200_CHECK_ARG(naxes >= 1 && naxes <= B200_MAX_AXES, "apply_diag_multi: bad axis count");
   B200_CHECK_ARG(D >= 1 && D <= B200_MAX_CUTOFF && total >= 1 && nbatch >= 1, "apply_diag_multi: bad geometry");
   for (int k = 0; k < naxes; ++k) B200_CHECK_ARG(strides[k] >= 1, "apply_diag_multi: bad stride");
-  // L = D^j: the largest power of the cutoff that divides the state and fits the row table
+  // L = D^j: the largest power of the cutoff that divides the state and fits the row table; SUP = D rows
+  // form a super-row when the state allows
   long long Lr = 1;
   while (D > 1 && Lr * D <= DIAG_LOW_MAX && total % (Lr * D) == 0) Lr *= D;
-  for (int k = 0; k < naxes; ++k)
-    B200_CHECK_ARG(strides[k] < Lr ? Lr % (strides[k] * D) == 0 : strides[k] % Lr == 0,
+  const int SUP = (D > 1 && total % (Lr * D) == 0) ? D : 1;
+  int axisL = -1;
+  for (int k = 0; k < naxes; ++k) {
+    if (SUP > 1 && strides[k] == Lr) axisL = k;
+    B200_CHECK_ARG(strides[k] < Lr ? Lr % (strides[k] * D) == 0
+                                   : (strides[k] == Lr && SUP > 1) || strides[k] % (Lr * SUP) == 0,
                    "apply_diag_multi: axis stride does not tile the state");
-  const long long nrows = total / Lr;
-  long long want = nrows < 148 * 8 ? nrows : 148 * 8;
+  }
+  const long long nsuper = total / (Lr * SUP);
+  long long want = nsuper < 148 * 8 ? nsuper : 148 * 8;
   dim3 grid((unsigned)want, 1, nbatch);
   size_t smem = ((size_t)naxes * D + (size_t)Lr) * sizeof(cplx);
   if (total < (1ll << 32)) {
@@ -559,7 +538,7 @@ int b200_apply_diag_multi(b200_c128* state_dev, int64_t total, int D, int naxes,
       md.conj[k] = conj_flags[k];
     }
     k_apply_diag_multi<unsigned><<<grid, 256, smem, (cudaStream_t)stream>>>(
-        (cplx*)state_dev, (unsigned)nrows, (int)Lr, D, md, (const cplx*)tabs_dev, state_batch_stride,
+        (cplx*)state_dev, (unsigned)nsuper, SUP, (int)Lr, D, axisL, md, (const cplx*)tabs_dev, state_batch_stride,
         tab_batch_stride);
   } else {
     DiagAxes<unsigned long long> md;
@@ -569,8 +548,8 @@ int b200_apply_diag_multi(b200_c128* state_dev, int64_t total, int D, int naxes,
       md.conj[k] = conj_flags[k];
     }
     k_apply_diag_multi<unsigned long long><<<grid, 256, smem, (cudaStream_t)stream>>>(
-        (cplx*)state_dev, (unsigned long long)nrows, (int)Lr, D, md, (const cplx*)tabs_dev, state_batch_stride,
-        tab_batch_stride);
+        (cplx*)state_dev, (unsigned long long)nsuper, SUP, (int)Lr, D, axisL, md, (const cplx*)tabs_dev,
+        state_batch_stride, tab_batch_stride);
   }
   return cuda_status("apply_diag_multi");
 }

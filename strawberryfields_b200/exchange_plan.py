@@ -26,7 +26,15 @@ from __future__ import annotations
 
 from itertools import combinations
 
-INNER_PENALTY = 2     # an exchange that evicts the innermost axis moves 16*D/p-byte runs: ~3x slower
+# Costs are in quarter exchanges.  What an exchange costs depends on the INNERMOST position it evicts: the
+# block copy moves contiguous runs of (elements behind that position) * 16 bytes.  Evicting the innermost
+# axis itself leaves 16*D/p-byte (80 B) runs -- measured ~3x slower over NVLink; the axis next to it leaves
+# 16*D-byte (160 B) runs -- measured 382 GB/s against 600-700 GB/s for runs of 1.6 KB and more (round 2:
+# bulk-copy exchange kernel, profiles/r02_xchg_probe.json).
+EXCHANGE_COST = 4
+INNER_PENALTY = 8     # evicting position n-1
+NEXT_PENALTY = 2      # evicting position n-2
+THIRD_PENALTY = 1     # evicting position n-3: 16*D*D-byte (1.6 KB) runs, measured 600 against 675-710 GB/s
 DEFAULT_BUDGET = 2500  # queue sweeps one plan() may spend (~5 us each for a 60-gate queue)
 _FAR = 1 << 30
 
@@ -59,7 +67,7 @@ def _swap(phys, g, T):
     return phys
 
 
-def _belady(op_axes, order, phys, g):
+def _belady(op_axes, order, phys, g, keep_runs_long=True):
     """Positions to evict by the online rule; ``order`` is the blocked remainder of the queue."""
     n = len(phys)
     next_use = {}
@@ -72,16 +80,29 @@ def _belady(op_axes, order, phys, g):
     cand = [p for p in range(g, n) if phys[p] not in need]
     if len(cand) < g:
         raise ValueError("a %d-mode state has too few whole axes to exchange %d sharded ones" % (n, g))
-    if len([p for p in cand if p != n - 1]) >= g:
-        cand = [p for p in cand if p != n - 1]
+    # keep the runs of the block copy long when there is a choice (positions are not final while the layout
+    # of a fresh state is still being chosen: then only the innermost axis is avoided)
+    for avoid in ((n - 1, n - 2, n - 3), (n - 1, n - 2), (n - 1,)) if keep_runs_long else ((n - 1,),):
+        if len([p for p in cand if p not in avoid]) >= g:
+            cand = [p for p in cand if p not in avoid]
+            break
     far = sorted(((next_use.get(phys[p], _FAR), p) for p in cand), reverse=True)
     return sorted(p for _, p in far[:g])
 
 
-def greedy(op_axes, phys, g, left=None):
+def exchange_cost(T, n, penalty=True):
+    """cost of one exchange that evicts the (sorted) positions ``T`` of an ``n``-axis layout"""
+    if not penalty:
+        return EXCHANGE_COST
+    last = T[-1]
+    return EXCHANGE_COST + (INNER_PENALTY if last == n - 1 else NEXT_PENALTY if last == n - 2 else
+                            THIRD_PENALTY if last == n - 3 else 0)
+
+
+def greedy(op_axes, phys, g, left=None, keep_runs_long=True):
     """The online plan.  Returns (cost, steps): steps are ``("run", [i, ..])`` /
-    ``("exchange", (evicted modes))``; cost counts exchanges (+ INNER_PENALTY for each one that
-    evicts the innermost axis)."""
+    ``("exchange", (evicted modes))``; cost = sum of ``exchange_cost`` (quarter exchanges, with the
+    penalties for short runs)."""
     phys = list(phys)
     n = len(phys)
     masks = [_mask(a) for a in op_axes]
@@ -95,15 +116,15 @@ def greedy(op_axes, phys, g, left=None):
             steps.append(("run", run))
         if not order:
             return cost, steps
-        T = _belady(op_axes, order, phys, g)
-        cost += 1 + (INNER_PENALTY if n - 1 in T else 0)
+        T = _belady(op_axes, order, phys, g, keep_runs_long)
+        cost += exchange_cost(T, n, keep_runs_long)
         steps.append(("exchange", tuple(phys[p] for p in T)))
         phys = _swap(phys, g, T)
 
 
-def search(op_axes, phys, g, left, penalty=INNER_PENALTY, bound=None):
-    """Cheapest plan found by a depth-first search from layout ``phys`` (cost = number of
-    exchanges, plus ``penalty`` for every one that evicts the innermost axis); ``left[0]`` is the
+def search(op_axes, phys, g, left, penalty=True, bound=None):
+    """Cheapest plan found by a depth-first search from layout ``phys`` (cost = sum of
+    ``exchange_cost``; ``penalty=False`` counts exchanges only); ``left[0]`` is the
     remaining sweep budget, shared with the caller.  Returns (cost, steps), or None when nothing
     cheaper than ``bound`` was found."""
     n = len(phys)
@@ -120,15 +141,15 @@ def search(op_axes, phys, g, left, penalty=INNER_PENALTY, bound=None):
             if cost < best[0]:
                 best[0], best[1] = cost, trail
             return
-        if cost + 1 >= best[0] or left[0] <= 0:
+        if cost + EXCHANGE_COST >= best[0] or left[0] <= 0:
             return
-        key = (tuple(rest), _mask(phys[:g]), phys[n - 1])
+        key = (tuple(rest), _mask(phys[:g]), phys[n - 1], phys[n - 2], phys[n - 3])
         if seen.get(key, _FAR) <= cost:
             return
         seen[key] = cost
         opts = []
         for T in combinations(range(g, n), g):
-            c = 1 + (penalty if T[-1] == n - 1 else 0)
+            c = exchange_cost(T, n, penalty)
             if cost + c >= best[0]:
                 continue
             if left[0] <= 0:
@@ -169,6 +190,18 @@ def replicated_prefix(op_axes, k_max):
     return rep, rest
 
 
+def plan_cost(phys0, g, steps):
+    """cost of a plan, with the short-run penalties, when it starts from layout ``phys0``"""
+    phys, n, cost = list(phys0), len(phys0), 0
+    for s in steps:
+        if s[0] == "exchange":
+            pos = {m: p for p, m in enumerate(phys)}
+            T = sorted(pos[m] for m in s[1])
+            cost += exchange_cost(T, n)
+            phys = _swap(phys, g, T)
+    return cost
+
+
 def exchanges(steps):
     return sum(1 for s in steps if s[0] == "exchange")
 
@@ -193,8 +226,8 @@ def plan(op_axes, phys, g, free_layout=False, budget=DEFAULT_BUDGET):
     if not free_layout or exchanges(base) == 0:
         return phys, base
 
-    # ---- vacuum: choose the initially sharded modes, then the innermost mode; the given layout is
-    # kept unless another one saves at least one exchange ----
+    # ---- vacuum: choose the initially sharded modes, then the two innermost modes; the given sharded set
+    # is kept unless another one saves at least one exchange ----
     def layout(sh):
         return list(sh) + [m for m in phys if m not in sh]
 
@@ -204,37 +237,41 @@ def plan(op_axes, phys, g, free_layout=False, budget=DEFAULT_BUDGET):
         if left[0] <= budget // 3:  # keep at least a third of the budget for the searches
             break
         try:
-            starts.append((greedy(op_axes, layout(sh), g, left)[0], sh))
+            starts.append((greedy(op_axes, layout(sh), g, left, keep_runs_long=False)[0], sh))
         except ValueError:
             continue
     starts.sort()
-    best = (exchanges(base), None, None)
+    best = (exchanges(base) * EXCHANGE_COST, base, tuple(phys[:g]))
     for _, sh in starts[:4]:
         if left[0] <= 0:
             break
-        # positions are not final yet: search without the innermost penalty, fix the layout afterwards
-        found = search(op_axes, layout(sh), g, left, penalty=0, bound=best[0])
+        # positions are not final yet: search without the short-run penalties, fix the layout afterwards
+        found = search(op_axes, layout(sh), g, left, penalty=False, bound=best[0])
         if found is not None:
             best = (found[0], found[1], sh)
-    if best[1] is None:
-        return phys, base
     _, steps, sh = best
-    evicted = set(sh)
-    for s in steps:
-        if s[0] == "exchange":
-            evicted.update(s[1])
     uses = {m: 0 for m in phys}
     for a in op_axes:
         for m in a:
             uses[m] += 1
+    # A plan names the modes every exchange evicts, so it is valid for ANY order of the whole axes; the
+    # order decides which positions the exchanges touch.  Innermost axis: a mode that is never exchanged,
+    # the least-used one (the streaming kernels are slowest on the last axis); the axis next to it: a mode
+    # that keeps the exchanges away from the two innermost positions, where the runs of the block copy
+    # are short; everything else keeps ascending order.
     rest = [m for m in phys if m not in sh]
-    # innermost axis: a mode that is never exchanged, the least-used one (the streaming kernels are
-    # slowest on the last axis); everything else keeps ascending order
-    stay = sorted((m for m in rest if m not in evicted), key=lambda m: (-uses[m], m))
-    if stay:
-        last = stay[-1]
-        rest = [m for m in rest if m != last] + [last]
-    return list(sh) + rest, steps
+    if len(rest) < 3:
+        return list(sh) + rest, steps
+    choice = None
+    for last in rest:
+        for nxt in rest:
+            if nxt == last:
+                continue
+            lay = list(sh) + [m for m in rest if m not in (last, nxt)] + [nxt, last]
+            key = (plan_cost(lay, g, steps), uses[last], uses[nxt], last, nxt)
+            if choice is None or key < choice[0]:
+                choice = (key, lay)
+    return choice[1], steps
 
 
 def check(op_axes, phys0, g, steps):

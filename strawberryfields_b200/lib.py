@@ -14,7 +14,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libb200fock.so")
 
 MAX_AXES = 24
-MAX_CUTOFF = 64
+MAX_CUTOFF = 64        # single-mode and diagonal gates, reductions
+MAX_PAIR_CUTOFF = 27   # two-mode gates / loss channel: the packed table must fit 227 KB of shared memory
+MAX_BATCH = 65535      # the batch axis is gridDim.z
 
 # gate kinds / rules (mirror include/b200fock.h)
 GATE_DISPLACEMENT, GATE_SQUEEZE = 1, 2
@@ -57,6 +59,34 @@ class TileOp(C.Structure):
     ]
 
 
+XCHG_MAX_AXES = 12
+XCHG_MAX_PEERS = 32
+
+
+class XchgDesc(C.Structure):
+    _fields_ = [
+        ("n_axes", C.c_int),
+        ("n_src", C.c_int),
+        ("first_src", C.c_int),
+        ("ext", C.c_int32 * XCHG_MAX_AXES),
+        ("ss", C.c_int64 * XCHG_MAX_AXES),
+        ("ds", C.c_int64 * XCHG_MAX_AXES),
+        ("run", C.c_int64),
+        ("src", C.c_void_p * XCHG_MAX_PEERS),
+        ("dst", C.c_void_p * XCHG_MAX_PEERS),
+        ("src_base", C.c_int64 * XCHG_MAX_PEERS),
+        ("dst_base", C.c_int64 * XCHG_MAX_PEERS),
+    ]
+
+
+class PeerFlags(C.Structure):
+    _fields_ = [
+        ("n_ranks", C.c_int),
+        ("rank", C.c_int),
+        ("flags", C.c_void_p * XCHG_MAX_PEERS),
+    ]
+
+
 TILE_DIAG = 3
 TILE_MAX_OPS = 16
 MAX_FAST_CUTOFF = 16
@@ -93,6 +123,8 @@ SIGNATURES = {
     "b200_abs2": [_P, _P, _L, _P],
     "b200_norm2": [_P, _L, _P, _P, _P],
     "b200_scale": [_P, _L, _D, _D, _P, _I, _P],
+    "b200_exchange_copy": [C.POINTER(XchgDesc), _I, _I, _P],
+    "b200_peer_barrier": [C.POINTER(PeerFlags), C.c_uint64, _D, _P],
 }
 _RESTYPES = {
     "b200_last_error": C.c_char_p,

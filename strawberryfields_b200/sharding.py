@@ -29,6 +29,8 @@ on 8 ranks.
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -139,14 +141,21 @@ class ShardedCircuit(DeviceCircuit):
     def _canonicalize(self):  # the sharded layout is never canonical; readers go through _stride()
         return
 
+    _FLAG_PAD = 64  # complex128 entries behind every state buffer; buffer 0's hold the barrier counters
+
     def _alloc(self):
         """(Re)allocate the two ping-pong state buffers for the current geometry and map them into the
-        peers when possible.  Collective."""
+        peers when possible.  Collective.  A buffer that a state object returned earlier still shares
+        (copy-on-write snapshots of the NCCL mode) is never reused: the reference's reset allocates a new
+        array too."""
         size = self._size()
-        if self._bufs is None or self._bufs[0].numel() != size:
+        if self._bufs is None or self._bufs[0].numel() != size or (getattr(self, "_shared", False) and not self._p2p):
             self._bufs = None
             self._buf = None
-            self._bufs = [self._new(size)]
+            self._backing = None
+            self._p2p = False
+            self._backing = [self._new(size + self._FLAG_PAD)]
+            self._bufs = [self._backing[0][:size]]
             self._p2p = self._setup_p2p(size)
         self._cur = 0
         self._buf = self._bufs[0]
@@ -212,6 +221,16 @@ class ShardedCircuit(DeviceCircuit):
         self._fresh = False
 
     def reset(self, pure=None, cutoff_dim=None, num_subsystems=None):
+        # same argument checks as DeviceCircuit.reset (circuit.py:89-116 of the reference)
+        if pure is not None and not isinstance(pure, bool):
+            raise ValueError("Argument 'pure' must be either True or False")
+        if num_subsystems is not None and not isinstance(num_subsystems, int):
+            raise ValueError("Argument 'num_subsystems' must be a positive integer")
+        if cutoff_dim is not None:
+            if not isinstance(cutoff_dim, int) or cutoff_dim < 1:
+                raise ValueError("Argument 'cutoff_dim' must be a positive integer")
+            if cutoff_dim > L.MAX_CUTOFF:
+                raise ValueError("b200fock supports cutoff_dim <= {}".format(L.MAX_CUTOFF))
         if num_subsystems is not None:
             self._num_modes = num_subsystems
         if cutoff_dim is not None:
@@ -220,6 +239,9 @@ class ShardedCircuit(DeviceCircuit):
             self._trunc = cutoff_dim
         if pure is not None:
             self._pure = bool(pure)
+        if self._g > self._axes() - 1:
+            raise ValueError("%d modes are too few to shard over %d ranks at cutoff %d"
+                             % (self._num_modes, self._world, self._trunc))
         self._phys = list(range(self._axes()))
         self._pos = list(range(self._axes()))
         self._alloc()
@@ -343,6 +365,7 @@ class ShardedCircuit(DeviceCircuit):
         that are still untouched, straight into the layout the exchange planner chose for the rest."""
         n, D, g = self._num_modes, self._trunc, self._g
         rep = DeviceCircuit(n, D, pure=True, device=self.device, fuse="fold", lazy_vacuum=True)
+        rep._defer_log = None  # the operators below are already in execution order: apply them as they come
         if self.__dict__.get("profile") is not None:
             rep.profile = self.profile
         for op in ops:
@@ -405,22 +428,27 @@ class ShardedCircuit(DeviceCircuit):
     # ------------------------------------------------------------------ peer mapping (NVLink P2P)
     def _setup_p2p(self, size):
         """Map both state buffers of every rank into this process (CUDA IPC through torch's storage
-        sharing) and enable peer access, so that a kernel here can read a peer's shard directly.
-        Collective; returns True only if it worked on every rank."""
+        sharing) and enable peer access, so that a kernel here can read (or write) a peer's shard
+        directly.  Every buffer is followed by a small pad; buffer 0's pad holds the counters of the
+        device-side barrier (``b200_peer_barrier``).  Collective; returns True only if it worked on
+        every rank."""
         if self._xmode == "nccl" or self._world == 1:
             return False
         if self.device.type != "cuda":
-            # CPU test double (gloo tests, exchange="p2p" only): the "peer memory" is POSIX shared memory,
-            # so the pull logic below -- bases, strides, ping-pong, barriers -- runs without a GPU
+            # CPU test double (gloo tests, exchange="p2p" / "push" only): the "peer memory" is POSIX shared
+            # memory, so the exchange logic below -- bases, strides, ping-pong -- runs without a GPU
             return self._xmode in ("p2p", "push") and self._setup_shared_host(size)
         ok = True
         peers = None
+        total = size + self._FLAG_PAD
         # Every collective below is reached by every rank whatever fails locally (a rank that bailed
         # out early would leave the others waiting in all_gather_object).
         shared = None
         try:
-            self._bufs.append(self._new(size))
-            shared = [(b.untyped_storage()._share_cuda_(), b.storage_offset()) for b in self._bufs]
+            self._backing.append(self._new(total))
+            self._bufs.append(self._backing[1][:size])
+            L.call("b200_fill_zero", C.c_void_p(self._backing[0].data_ptr() + 16 * size), self._FLAG_PAD, self._stream())
+            shared = [(b.untyped_storage()._share_cuda_(), b.storage_offset()) for b in self._backing]
         except Exception as exc:
             ok = False
             self._p2p_error = repr(exc)
@@ -433,7 +461,7 @@ class ShardedCircuit(DeviceCircuit):
             for r, (dev, sh) in enumerate(everyone):
                 for i in range(2):
                     if r == self._rank:
-                        peers[i][r] = self._bufs[i]
+                        peers[i][r] = self._backing[i]
                         continue
                     L.call("b200_enable_peer_access", int(dev))
                     handle, offset = sh[i]
@@ -442,88 +470,131 @@ class ShardedCircuit(DeviceCircuit):
                     handle = (self.device.index,) + tuple(handle[1:])
                     st = torch.UntypedStorage._new_shared_cuda(*handle)
                     typed = torch.storage.TypedStorage(wrap_storage=st, dtype=torch.complex128, _internal=True)
-                    peers[i][r] = torch._utils._rebuild_tensor(typed, offset, (size,), (1,))
+                    peers[i][r] = torch._utils._rebuild_tensor(typed, offset, (total,), (1,))
         except Exception as exc:  # no IPC / no peer path on this box: fall back to the NCCL exchange
             ok = False
             self._p2p_error = repr(exc)
+        self._sync()  # the barrier counters are zero before any peer can bump them
         flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.device)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self._pg)
         ok = bool(flag.item())
         if ok:
             self._peers = peers
+            self._epoch = 0
+            pf = L.PeerFlags()
+            pf.n_ranks, pf.rank = self._world, self._rank
+            for r in range(self._world):
+                pf.flags[r] = peers[0][r].data_ptr() + 16 * size
+            self._pflags = pf
         else:
             if self._xmode in ("p2p", "push"):
                 raise L.B200Error("peer-memory exchange requested but not available: %s"
                                   % getattr(self, "_p2p_error", "a peer failed"))
             self._bufs = self._bufs[:1]
+            self._backing = self._backing[:1]
             self._peers = None
         return ok
 
     def _setup_shared_host(self, size):
-        self._bufs = [self._new(size).share_memory_() for _ in range(2)]
-        shared = [(b.untyped_storage()._share_filename_cpu_(), b.storage_offset()) for b in self._bufs]
+        total = size + self._FLAG_PAD
+        self._backing = [self._new(total).share_memory_() for _ in range(2)]
+        self._bufs = [b[:size] for b in self._backing]
+        shared = [(b.untyped_storage()._share_filename_cpu_(), b.storage_offset()) for b in self._backing]
         everyone = [None] * self._world
         dist.all_gather_object(everyone, shared, group=self._pg)
         self._peers = [[None] * self._world for _ in range(2)]
         for r, sh in enumerate(everyone):
             for i in range(2):
                 if r == self._rank:
-                    self._peers[i][r] = self._bufs[i]
+                    self._peers[i][r] = self._backing[i]
                     continue
                 handle, offset = sh[i]
                 st = torch.UntypedStorage._new_shared_filename_cpu(*handle)
-                self._peers[i][r] = torch.empty(0, dtype=torch.complex128).set_(st, offset, (size,), (1,))
+                self._peers[i][r] = torch.empty(0, dtype=torch.complex128).set_(st, offset, (total,), (1,))
+        self._epoch = 0
         return True
 
     def _sync(self):
         if self.device.type == "cuda":
             torch.cuda.synchronize(self.device)
 
+    def _peer_barrier(self):
+        """Every rank's stream has reached this point: a stream-ordered barrier kernel over peer-mapped
+        counters -- the host neither synchronises nor blocks.  (CPU double: the process group.)"""
+        self._epoch += 1
+        if self.device.type != "cuda":
+            dist.barrier(group=self._pg)
+            return
+        L.call("b200_peer_barrier", C.byref(self._pflags), self._epoch, 60.0, self._stream())
+
     def _exchange_p2p(self, T):
-        """Exchange without staging: for every source rank, ONE strided-gather launch reads that
-        rank's block of the old layout straight out of its HBM over NVLink and writes it where it
-        belongs in this rank's new shard (the other ping-pong buffer)."""
+        """Exchange without staging buffers and without host stalls: after a device-side barrier ONE launch
+        (``b200_exchange_copy``) moves this rank's whole share -- for every source rank a strided block of
+        the old layout goes where it belongs in the new shard (the other ping-pong buffer), sources
+        interleaved so that every NVLink peer is busy at once.  "p2p" pulls (the peers' old shards are the
+        sources), "push" posts stores into the peers' new shards."""
         g, n, D = self._g, self._axes(), self._trunc
         size = self._size()
         ls = [self._local_stride(p) for p in range(n)]
         sub = [D // p for p in self._ps]
         prof = self.__dict__.get("profile")
         push = self._xmode == "push"
-        # pull: every rank's current shard is final and may be read.  push: every rank has stopped using
-        # its other ping-pong buffer (a slower rank may still be reading it in _project_reset)
-        self._sync()
-        dist.barrier(group=self._pg)
         if prof is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
+        # pull: every rank's current shard is final and nobody still reads this rank's other buffer (it was
+        # the source of the previous exchange).  push: nobody still uses the buffer the peers will write.
+        self._peer_barrier()
         dst = self._bufs[1 - self._cur]
-        oa = []
+        axes = []  # (extent, source stride, destination stride), outermost first
         for pos in range(n):
             if pos < g:                       # new sharded remainder m_k <- source axis T[k]
-                oa.append((sub[pos], ls[T[pos]], 0, ls[pos]))
+                axes.append((sub[pos], ls[T[pos]], ls[pos]))
             elif pos in T:                    # new local axis T[k] <- source's remainder j_k on axis k
                 k = T.index(pos)
-                oa.append((sub[k], ls[k], 0, ls[pos]))
+                axes.append((sub[k], ls[k], ls[pos]))
             else:
-                oa.append((D, ls[pos], 0, ls[pos]))
+                axes.append((D, ls[pos], ls[pos]))
+        merged = []
+        for a in axes:
+            if a[0] == 1:
+                continue
+            if merged and merged[-1][1] == a[1] * a[0] and merged[-1][2] == a[2] * a[0]:
+                merged[-1] = (merged[-1][0] * a[0], a[1], a[2])
+            else:
+                merged.append(a)
+        run = 1
+        if merged and merged[-1][1] == 1 and merged[-1][2] == 1:
+            run = merged.pop()[0]
+        if len(merged) > L.XCHG_MAX_AXES or self._world > L.XCHG_MAX_PEERS:
+            raise L.B200Error("exchange geometry exceeds the copy kernel's limits")
+
         def block(digits):
             return sum(digits[k] * sub[k] * ls[T[k]] for k in range(g))
 
-        for step in range(self._world):
-            s = (self._rank + step) % self._world   # start with the local block, then walk the ring
+        d = L.XchgDesc()
+        d.n_axes, d.n_src, d.first_src, d.run = len(merged), self._world, self._rank, run
+        for j, (e, a, b) in enumerate(merged):
+            d.ext[j], d.ss[j], d.ds[j] = e, a, b
+        span_s = sum((e - 1) * a for e, a, _ in merged) + run - 1
+        span_d = sum((e - 1) * b for e, _, b in merged) + run - 1
+        for s in range(self._world):
             sd = self._digits_of(s)
-            if push:
-                # posted remote stores: my block for rank s goes straight into ITS new shard
-                self._gather(self._buf, None, self._peers[1 - self._cur][s], oa,
-                             base=(block(sd), 0, block(self._digits)))
-            else:
-                # remote loads: the receiver's digit selects the block, the sender's digit lands on axis T[k]
-                self._gather(self._peers[self._cur][s], None, dst, oa, base=(block(self._digits), 0, block(sd)))
+            if push:   # my block for rank s goes straight into ITS new shard
+                d.src[s], d.dst[s] = self._buf.data_ptr(), self._peers[1 - self._cur][s].data_ptr()
+                d.src_base[s], d.dst_base[s] = block(sd), block(self._digits)
+            else:      # the receiver's digit selects the block, the sender's digit lands on axis T[k]
+                d.src[s], d.dst[s] = self._peers[self._cur][s].data_ptr(), dst.data_ptr()
+                d.src_base[s], d.dst_base[s] = block(self._digits), block(sd)
+            if d.src_base[s] + span_s >= size or d.dst_base[s] + span_d >= size:
+                raise L.B200Error("exchange block of rank %d leaves the shard" % s)
+        # this rank's own block stays in local HBM: plain copy by the CTAs the link does not need
+        L.call("b200_exchange_copy", C.byref(d), self._rank, int(self.__dict__.get("exchange_ctas", 0)),
+               self._stream())
+        if push:
+            self._peer_barrier()  # every peer's stores into my new shard have landed
         if prof is not None:
             ev1.record()
-        self._sync()
-        dist.barrier(group=self._pg)  # nobody still reads the old shards
-        if prof is not None:
             nbytes = 16 * size * (self._world - 1) // self._world
             prof.append(("exchange/p2p_push" if push else "exchange/p2p_pull", nbytes, ev0, ev1))
             prof.append(("exchange", nbytes, ev0, ev1))
@@ -762,6 +833,7 @@ class ShardedCircuit(DeviceCircuit):
         assert all(self._pos[a] >= self._g for ax in axes_of.values() for a in ax)
         self._fresh = False
         if self._p2p:
+            self._peer_barrier()  # a slower peer may still be pulling from the other ping-pong buffer
             out = self._bufs[1 - self._cur]
         else:
             out = self._get_scratch(self._buf.numel())

@@ -67,6 +67,24 @@ def main():
         ob.prepare_ket_state(ket, list(range(n)))
     W.run_calls(be, calls + extra)
     st = be.state()
+    if "reset" in flags:
+        # a state object handed out BEFORE reset() keeps its state (the reference's reset allocates a new
+        # array; ADVICE round 1: the NCCL mode used to zero the buffer the snapshot shared)
+        p_before = st.fock_prob([0] * n)
+        tr_before = st.trace()
+        be.reset()
+        ok = bool(abs(st.fock_prob([0] * n) - p_before) < 1e-15 and abs(st.trace() - tr_before) < 1e-15
+                  and abs(be.state().fock_prob([0] * n) - 1.0) < 1e-15 and p_before < 0.999)
+        for bad in ({"pure": 1}, {"cutoff_dim": 0}, {"num_subsystems": 2.5}):
+            try:
+                be.circuit.reset(**bad)
+                ok = False
+            except ValueError:
+                pass
+        print(json.dumps({"rank": dist.get_rank(), "world": dist.get_world_size(), "ok": ok}))
+        dist.barrier()
+        dist.destroy_process_group()
+        sys.exit(0 if ok else 1)
     from strawberryfields_b200 import sharding
 
     first_layout = list(next(iter(sharding._PLANS.values()))[0])  # layout the planner chose for |0..0>

@@ -374,3 +374,25 @@ class FakeLib:
         _c(p, n)[:] *= f
         self.launches += 1
         return 0
+
+    # -- multi-GPU exchange (the "peers" of the CPU double are POSIX shared-memory tensors)
+    def b200_exchange_copy(self, desc, local_src, bulk_ctas, stream):
+        d = desc._obj
+        exts = [d.ext[j] for j in range(d.n_axes)] + [int(d.run)]
+        ss = [d.ss[j] for j in range(d.n_axes)] + [1]
+        ds = [d.ds[j] for j in range(d.n_axes)] + [1]
+        so = np.zeros(1, dtype=np.int64)
+        do = np.zeros(1, dtype=np.int64)
+        for e, a, b in zip(exts, ss, ds):
+            so = (so[:, None] + (np.arange(e, dtype=np.int64) * a)[None, :]).reshape(-1)
+            do = (do[:, None] + (np.arange(e, dtype=np.int64) * b)[None, :]).reshape(-1)
+        assert len(np.unique(do)) == len(do), "exchange destinations overlap"
+        for k in range(d.n_src):
+            s = (k + d.first_src) % d.n_src
+            si, di = so + d.src_base[s], do + d.dst_base[s]
+            _c(d.dst[s], int(di.max()) + 1)[di] = _c(d.src[s], int(si.max()) + 1)[si]
+        self.launches += 1
+        return 0
+
+    def b200_peer_barrier(self, pf, epoch, timeout_s, stream):
+        raise AssertionError("the CPU double synchronises with the process group, not with device flags")

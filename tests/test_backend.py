@@ -34,6 +34,7 @@ def host_backend(request, monkeypatch):
         orig = be.begin_circuit
 
         def begin(n, **kw):
+            kw.setdefault("lazy_vacuum", False)  # the eager path; tests/test_vacuum_lazy.py runs the default
             kw.update(opts)
             return orig(n, **kw)
 

@@ -41,7 +41,8 @@ def bench(monkeypatch):
 
 def _args(**kw):
     base = dict(gpus=1, steps=2, warmup=1, impl="b200", modes=4, cutoff=3, no_cpu_baseline=True, workload="c2",
-                batch=2, exchange="auto", fuse="fold", from_vacuum=False)
+                batch=2, exchange="auto", fuse="fold", from_vacuum=False, no_parity=False, no_ten_mode=False,
+                parity_probs=12)
     base.update(kw)
     return argparse.Namespace(**base)
 
@@ -102,6 +103,11 @@ def test_sharded_arm(exchange, mode):
     for key in CONTRACT:
         assert key in line, key
     assert line["n_gpus"] == 2 and line["scaling"] == "strong"
+    # the sharded arm proves its own correctness in the line: single-photon transfer, comparison with an
+    # unsharded run of the same circuit on rank 0, seeded MeasureFock
+    assert line["parity"]["max_abs_err"] <= 1e-12 and line["parity"]["measure_equal"]
+    assert line["parity"]["vs_unsharded_run_on_rank0"]["fock_probs_compared"] == 12
+    assert line["single_gpu_same_workload_ms"] > 0 and line["strong_efficiency"] > 0
     if not mode:  # from vacuum the replicated prefix may leave nothing to exchange at this size
         assert line["exchange"]["all_to_all_per_step"] >= 1
         assert ("p2p_" in " ".join(line["exchange"])) == (exchange != "auto")

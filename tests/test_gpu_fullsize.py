@@ -166,3 +166,82 @@ def test_config4_size_batched_layer_vs_oracle():
             args = [x[b] if isinstance(x, np.ndarray) else x for x in c[1:]]
             getattr(ob, c[0])(*args)
         assert np.abs(kets[b] - ob.state().data).max() < TOL
+
+
+# ---------------------------------------------------------------------------- full-size oracle fixtures
+# tests/golden/ref_config{2,3}_full.npz: the oracle (vector style) run ONCE at the BASELINE sizes by
+# oracle/make_golden_fullsize.py -- sampled amplitudes / density-matrix entries, every single-mode
+# marginal, the trace and (config 3) seeded MeasureFock outcomes.  1e-12 absolute, outcomes exact.
+def _golden(name):
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name)
+    if not os.path.exists(path):
+        pytest.skip("%s not generated (python -m oracle.make_golden_fullsize)" % name)
+    return np.load(path)
+
+
+def _sampled_entries(circ, idx):
+    """entries of the device tensor at the multi-indices ``idx`` [count, axes] (one D2H copy)"""
+    import torch
+
+    circ._flush()
+    lin = np.zeros(len(idx), dtype=np.int64)
+    for ax in range(idx.shape[1]):
+        lin += idx[:, ax] * circ._stride(ax)
+    return circ._buf[torch.from_numpy(lin).to(circ._buf.device)].cpu().numpy()
+
+
+@pytest.mark.parametrize("opts", [{"lazy_vacuum": False}, {"lazy_vacuum": True}, {"lazy_vacuum": False, "fuse": "tile"}],
+                         ids=["eager", "lazy", "tile"])
+def test_config2_full_size_matches_oracle_fixture(opts):
+    """BASELINE config 2 at full size: 10 000 sampled amplitudes, all marginals and the norm equal the
+    oracle's (the run bench.py times)."""
+    ref = _golden("ref_config2_full.npz")
+    n, D = int(ref["n_modes"]), int(ref["cutoff"])
+    calls = W.config2_circuit(n, seed=42)
+    assert len(calls) == int(ref["gates"])
+    be = _backend(n=n, cutoff_dim=D, **opts)
+    W.run_calls(be, calls)
+    st = be.state()
+    amp = _sampled_entries(st._view, ref["idx"])
+    assert np.abs(amp - ref["amp"]).max() < TOL
+    assert abs(st.trace() - float(ref["trace"])) < TOL
+    marg = np.stack([st._view.marginal_probs_device([m])[0].cpu().numpy() for m in range(n)])
+    # a marginal is a sum of 1e7 probabilities: the two summation orders (numpy's strided sum, the device tree)
+    # differ by ~1e-12 relative; amplitudes and individual probabilities above are held to 1e-12
+    assert np.abs(marg - ref["marg"]).max() < 1e-11
+
+
+@pytest.mark.parametrize("lazy", [False, True], ids=["eager", "lazy"])
+def test_config3_full_size_matches_oracle_fixture(lazy):
+    """BASELINE config 3 at full size (4-mode density matrix, 1e8 entries, loss on every mode): sampled
+    entries of rho, the diagonal, the marginals and the trace equal the oracle's; the seed-7 MeasureFock on
+    all modes and eight more seeds give the oracle's outcomes exactly."""
+    ref = _golden("ref_config3_full.npz")
+    n, D = int(ref["n_modes"]), int(ref["cutoff"])
+    calls = W.config3_circuit(n, seed=42)
+    be = _backend(n=n, cutoff_dim=D, pure=False, lazy_vacuum=lazy)
+    W.run_calls(be, calls)
+    st = be.state()
+    assert not st.is_pure
+    assert np.abs(_sampled_entries(st._view, ref["idx"]) - ref["amp"]).max() < TOL
+    assert abs(st.trace() - complex(ref["trace"]).real) < TOL
+    probs = st.all_fock_probs()
+    assert np.abs(probs[tuple(ref["diag_idx"].T)] - ref["diag_prob"]).max() < TOL
+    assert np.abs(probs.reshape(-1)[ref["top_idx"]] - ref["top_prob"]).max() < TOL
+    marg = np.stack([probs.sum(axis=tuple(a for a in range(n) if a != m)) for m in range(n)])
+    assert np.abs(marg - ref["marg"]).max() < 1e-11
+    if "extra_seeds" in ref:
+        for sd, want in zip(ref["extra_seeds"], ref["extra_outcomes"]):
+            b2 = _backend(n=n, cutoff_dim=D, pure=False, lazy_vacuum=lazy)
+            W.run_calls(b2, calls)
+            np.random.seed(int(sd))
+            assert np.array_equal(np.asarray(b2.measure_fock(list(range(n)))).reshape(-1), want), int(sd)
+            del b2
+    np.random.seed(int(ref["measure_seed"]))
+    got = be.measure_fock(list(range(n)))
+    assert np.array_equal(np.asarray(got), ref["outcome"])
+    post = be.state()
+    assert abs(post.trace() - complex(ref["post_trace"]).real) < TOL
+    assert abs(post.fock_prob([0] * n) - float(np.real(ref["post_prob_of_outcome"]))) < TOL

@@ -325,3 +325,100 @@ def test_tile_pass_batched_and_ragged(lib, torch_mod):
     FakeLib().b200_apply_tile_pass(C.c_void_p(want.ctypes.data), total, D, D ** 3, D ** 1, ops, 2, perm,
                                    C.c_void_p(cfh.ctypes.data), per, B, total, per, None)
     assert np.abs(st.cpu().numpy() - want).max() < 1e-11
+
+
+# ---------------------------------------------------------------------------- innermost-axis geometries
+# The TMA-staged persistent kernel (csrc/inner.cu) has one tile shape per geometry: adjacent axes (mid = 1),
+# a short mid (< 32 slices per row run: whole outer blocks), rows (mid >= 32), one-mode gates on the last
+# axis; partial tiles at the end of a state and of a row run; per-entry gate tables on a batch.
+@pytest.mark.parametrize("D,n", [(10, 5), (6, 6), (4, 7), (3, 7), (7, 4), (12, 4), (16, 3)])
+def test_inner_axis_pair_gates_all_partners(lib, torch_mod, D, n):
+    torch = torch_mod
+    rs = np.random.RandomState(17 * D + n)
+    psi = _rand(rs, *([D] * n))
+    for rule in ("sum", "diff"):
+        if rule == "sum":
+            T, kind, rl, args = og.beamsplitter(0.6, 0.3, D), lib.GATE_BEAMSPLITTER, lib.RULE_SUM, (0.6, 0.3)
+        else:
+            T, kind, rl, args = og.two_mode_squeeze(0.25, 0.9, D), lib.GATE_S2, lib.RULE_DIFF, (0.25, 0.9)
+        packed = torch.empty(lib.packed_size(D), dtype=torch.complex128, device="cuda")
+        lib.call("b200_gen_gate2", kind, D, 1, args[0], args[1], None, _p(packed), None)
+        for a in range(n - 1):
+            for (x, y) in ((a, n - 1), (n - 1, a)):
+                st = _dev(torch, psi.reshape(-1))
+                lib.call("b200_apply_gate2", _p(st), D ** n, D, D ** (n - 1 - x), D ** (n - 1 - y), rl,
+                         _p(packed), 0, 1, D ** n, 0, None)
+                want = np.moveaxis(np.tensordot(T, psi, axes=([1, 3], [x, y])), [0, 1], [x, y])
+                assert np.abs(st.cpu().numpy().reshape(psi.shape) - want).max() < 1e-11, (rule, x, y)
+
+
+@pytest.mark.parametrize("D,slices", [(10, 1000), (10, 333), (6, 4099), (5, 77), (16, 40), (2, 100001)])
+def test_inner_axis_one_mode_gate_ragged(lib, torch_mod, D, slices):
+    """one-mode gate on the innermost axis; slice counts that are not multiples of a tile"""
+    torch = torch_mod
+    rs = np.random.RandomState(D + slices)
+    psi = _rand(rs, slices, D)
+    U = _rand(rs, D, D)
+    st = _dev(torch, psi.reshape(-1))
+    lib.call("b200_apply_gate1", _p(st), slices, D, 1, _p(_dev(torch, U)), 1, 1, slices * D, 0, None)
+    want = psi @ U.conj().T
+    assert np.abs(st.cpu().numpy().reshape(psi.shape) - want).max() < 1e-11 * D
+
+
+def test_inner_axis_batched_tables(lib, torch_mod):
+    """per-entry gate tables on a batch: the persistent CTAs reload the table when their tile range crosses
+    into the next batch entry"""
+    torch = torch_mod
+    rs = np.random.RandomState(23)
+    D, B, n = 10, 5, 4
+    psi = _rand(rs, B, *([D] * n))
+    params = np.stack([rs.uniform(0, 1.5, B), rs.uniform(0, 6, B)])
+    P = lib.packed_size(D)
+    packed = torch.empty(B * P, dtype=torch.complex128, device="cuda")
+    lib.call("b200_gen_gate2", lib.GATE_BEAMSPLITTER, D, B, 0.0, 0.0, _p(_dev(torch, params)), _p(packed), None)
+    for (x, y) in ((2, 3), (3, 0), (1, 3)):
+        st = _dev(torch, psi.reshape(-1))
+        lib.call("b200_apply_gate2", _p(st), D ** n, D, D ** (n - 1 - x), D ** (n - 1 - y), lib.RULE_SUM, _p(packed),
+                 0, B, D ** n, P, None)
+        got = st.cpu().numpy().reshape(psi.shape)
+        for b in range(B):
+            T = og.beamsplitter(params[0, b], params[1, b], D)
+            want = np.moveaxis(np.tensordot(T, psi[b], axes=([1, 3], [x, y])), [0, 1], [x, y])
+            assert np.abs(got[b] - want).max() < 1e-11, (x, y, b)
+    U = _rand(rs, B, D, D)
+    st = _dev(torch, psi.reshape(-1))
+    lib.call("b200_apply_gate1", _p(st), D ** (n - 1), D, 1, _p(_dev(torch, U)), 0, B, D ** n, D * D, None)
+    want = np.einsum("bxy,b...y->b...x", U, psi)
+    assert np.abs(st.cpu().numpy().reshape(psi.shape) - want).max() < 1e-10
+
+
+def test_diag_multi_geometries(lib, torch_mod):
+    """b200_apply_diag_multi: super-row decomposition (rows of D^j elements, D rows per super-row) for axis
+    subsets that include / exclude the axis of stride L, conjugated entries, small states, a batch"""
+    torch = torch_mod
+    rs = np.random.RandomState(31)
+    for D, n, axes in ((10, 5, [0, 1, 4]), (10, 5, [1, 2]), (10, 5, [3]), (10, 4, [0, 1, 2, 3]), (7, 2, [0, 1]),
+                       (6, 6, [0, 2, 5]), (3, 1, [0]), (16, 3, [0, 2])):
+        psi = _rand(rs, *([D] * n))
+        tabs = np.exp(1j * rs.uniform(0, 6, (len(axes), D)))
+        conj = [int(rs.rand() < 0.5) for _ in axes]
+        want = psi.copy()
+        for t, ax, cj in zip(tabs, axes, conj):
+            shape = [1] * n
+            shape[ax] = D
+            want = want * (t.conj() if cj else t).reshape(shape)
+        st = _dev(torch, psi.reshape(-1))
+        k = len(axes)
+        strides = (C.c_int64 * k)(*[D ** (n - 1 - a) for a in axes])
+        conjs = (C.c_int * k)(*conj)
+        lib.call("b200_apply_diag_multi", _p(st), D ** n, D, k, strides, conjs, _p(_dev(torch, tabs.reshape(-1))), 1,
+                 D ** n, 0, None)
+        assert np.abs(st.cpu().numpy().reshape(psi.shape) - want).max() < TOL * 10, (D, n, axes)
+    D, n, B = 5, 4, 3
+    psi = _rand(rs, B, *([D] * n))
+    tabs = np.exp(1j * rs.uniform(0, 6, (B, 2, D)))
+    st = _dev(torch, psi.reshape(-1))
+    lib.call("b200_apply_diag_multi", _p(st), D ** n, D, 2, (C.c_int64 * 2)(D ** 3, D), (C.c_int * 2)(0, 1),
+             _p(_dev(torch, tabs.reshape(-1))), B, D ** n, 2 * D, None)
+    want = psi * tabs[:, 0].reshape(B, D, 1, 1, 1) * tabs[:, 1].conj().reshape(B, 1, 1, D, 1)
+    assert np.abs(st.cpu().numpy().reshape(psi.shape) - want).max() < TOL * 10

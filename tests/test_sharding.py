@@ -101,6 +101,13 @@ def test_sharded_density_matrices_match_oracle_gloo(world, n, D, exchange, flag)
     _run("host", world, n, D, exchange, flags=[flag])
 
 
+@pytest.mark.parametrize("exchange", ["auto", "p2p"])
+def test_state_object_survives_reset_gloo(exchange):
+    """eng.run() -> eng.reset() -> result.state: the snapshot keeps its buffer in every exchange mode, and
+    ShardedCircuit.reset validates its arguments like the single-GPU reset."""
+    _run("host", 2, 3, 4, exchange, flags=["reset"])
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("exchange", ["nccl", "p2p"])
 def test_sharded_circuit_matches_oracle_on_gpus(exchange):

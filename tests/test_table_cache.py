@@ -111,3 +111,33 @@ def test_cache_is_bounded():
         c.get(("k", i), lambda: torch.zeros(10, dtype=torch.complex128))
     assert len(c._d) <= 4
     assert ("k", 9) in c._d
+
+
+def test_limits_are_checked_up_front(counting):
+    """cutoffs 28..64 are accepted for single-mode work but a two-mode gate says clearly
+    that it is not supported (instead of a shared-memory opt-in failure mid-circuit); batch sizes beyond the
+    grid limit are refused at construction."""
+    from strawberryfields_b200.backend import B200FockBackend
+
+    be = B200FockBackend()
+    be.begin_circuit(2, cutoff_dim=30, lazy_vacuum=False)
+    be.rotation(0.3, 0)
+    with pytest.raises(ValueError, match="two-mode gates"):
+        be.beamsplitter(0.3, 0.1, 0, 1)
+    with pytest.raises(ValueError, match="two-mode gates"):
+        be.loss(0.5, 0)
+    with pytest.raises(ValueError, match="batch_size"):
+        B200FockBackend().begin_circuit(1, cutoff_dim=3, batch_size=70000)
+
+
+def test_batched_vacuum_and_norm_use_one_launch_each(counting):
+    from strawberryfields_b200.backend import B200FockBackend
+
+    be = B200FockBackend()
+    be.begin_circuit(2, cutoff_dim=4, batch_size=6, lazy_vacuum=False)
+    assert counting.calls["b200_set_element"] == 0           # no per-entry launches
+    be.displacement(np.linspace(0.1, 0.6, 6), 0.2, 0)
+    counting.calls.clear()
+    tr = be.state().trace()
+    assert counting.calls["b200_norm2"] == 0 and counting.calls["b200_gather_reduce"] >= 1
+    assert np.allclose(tr, 1.0, atol=1e-3) and np.shape(tr) == (6,)

@@ -216,6 +216,44 @@ def test_config2_full_size_passes_drop(backend, monkeypatch):
     assert kets[1] <= kets[3] - n  # at least the n single-mode passes are gone
 
 
+def test_deferred_program_puts_the_least_used_mode_innermost(backend, monkeypatch):
+    """Gate calls on a fresh lazy-vacuum circuit are recorded until the state is observed; the replay makes
+    the mode with the fewest two-mode gates the innermost tensor axis, so the Clements mesh of BASELINE
+    config 2 runs n/2 passes on the innermost axis instead of n (mode 1 used to end up there)."""
+    from strawberryfields_b200 import circuit
+    from strawberryfields_b200 import workloads as W
+
+    n, D = 6, 3
+    calls = W.config2_circuit(n, seed=42)
+    inner = []
+    orig = circuit.DeviceCircuit._k_gate2
+
+    def spy(self, G, rule, ax1, ax2, conj):
+        inner.append(min(self._stride(ax1), self._stride(ax2)) == 1 and self._size() == D ** n)
+        return orig(self, G, rule, ax1, ax2, conj)
+
+    monkeypatch.setattr(circuit.DeviceCircuit, "_k_gate2", spy)
+    be = backend()
+    be.begin_circuit(n, cutoff_dim=D)
+    W.run_calls(be, calls)
+    assert be.circuit._defer_log is not None and len(be.circuit._defer_log) == len(calls)  # nothing ran yet
+    assert not inner
+    ket = be.state().ket()
+    assert be.circuit._defer_log is None and be.circuit._inner_hint == 0
+    assert be.circuit._phys[-1] == 0          # mode 0 (n/2 beamsplitters) is the innermost axis
+    assert sum(inner) <= n // 2
+    ob = OracleBackend()
+    ob.begin_circuit(n, cutoff_dim=D)
+    W.run_calls(ob, calls)
+    assert np.abs(ket - ob.state().data).max() < TOL
+    # later calls are applied as they come, and a reset starts a new recording
+    be.beamsplitter(0.3, 0.2, 0, 1)
+    assert len(inner) > 0 and be.circuit._defer_log is None
+    be.reset()
+    be.rotation(0.2, 0)
+    assert be.circuit._defer_log == [("phase_shift", (0.2, 0))]
+
+
 @pytest.mark.gpu
 def test_full_size_config2_lazy_equals_eager_on_gpu():
     """BASELINE config 2 at full size (8 modes, cutoff 10, 1e8 amplitudes) from vacuum: the lazy-vacuum

@@ -2,13 +2,10 @@
 # 2-GPU validation of the sharded path (run as ONE gpurun --gpus 2 call from the repo root).
 set -u
 mkdir -p gpurun_out
-nvidia-smi -L > gpurun_out/r02_n2_gpus.txt 2>&1
-timeout 400 python -m pytest tests/test_sharding.py -q -m gpu 2>&1 | tail -15 > gpurun_out/r02_pytest_sharding_gpu_n2.log
-for ex in auto push nccl; do
+TAG=${1:-a}
+timeout 300 python -m pytest tests/test_sharding.py -q -m gpu -x 2>&1 | tail -15 > gpurun_out/r02${TAG}_pytest_sharding_gpu_n2.log
+for ex in auto push; do
   timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
       --master-port 29502 bench.py --gpus 2 --steps 5 --warmup 3 --exchange $ex --no-cpu-baseline \
-      > gpurun_out/r02_bench_n2_${ex}.json 2> gpurun_out/r02_bench_n2_${ex}.err
+      > gpurun_out/r02${TAG}_bench_n2_${ex}.json 2> gpurun_out/r02${TAG}_bench_n2_${ex}.err
 done
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
-    --master-port 29503 bench.py --gpus 2 --steps 5 --warmup 3 --from-vacuum --no-cpu-baseline \
-    > gpurun_out/r02_bench_n2_from_vacuum.json 2> gpurun_out/r02_bench_n2_from_vacuum.err
