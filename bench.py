@@ -471,7 +471,7 @@ def b200_arm(args):
     # the N GPUs (strong scaling), gates on sharded modes served by the all-to-all axis exchange.
     sharded = world > 1
     D = args.cutoff
-    shard_kw = {"shard": True, "exchange": args.exchange} if sharded else {}
+    shard_kw = {"shard": True, "exchange": args.exchange, "exchange_overlap": args.exchange_overlap} if sharded else {}
     if args.workload == "c3":      # BASELINE config 3: 4-mode MIXED state, S/BS layers + LossChannel(0.9)
         n_modes = args.modes or 4
         calls = W.config3_circuit(n_modes, seed=42)
@@ -728,6 +728,9 @@ def main():
     ap.add_argument("--fuse", default="fold", choices=["tile", "fold", "off"],
                     help="gate queue: diagonal / same-mode folding (default), + multi-gate tile passes, "
                          "or one pass per gate")
+    ap.add_argument("--exchange-overlap", type=int, default=8,
+                    help="sharded arm: gates behind an exchange that run part by part while the rest of the shard is "
+                         "still crossing NVLink (0 = off)")
     ap.add_argument("--no-parity", action="store_true", help="sharded arm: skip the parity block")
     ap.add_argument("--parity-probs", type=int, default=1000, help="sharded arm: Fock probabilities compared")
     ap.add_argument("--no-ten-mode", action="store_true", help="8-GPU sharded arm: skip the 10-mode / 160 GB block")

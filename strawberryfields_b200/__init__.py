@@ -15,6 +15,7 @@ from .autodiff import TorchCircuit  # noqa: F401
 from .backend import B200FockBackend, register  # noqa: F401
 from .circuit import DeviceCircuit, DeviceParams  # noqa: F401
 from .states import B200FockState  # noqa: F401
+from . import io  # noqa: F401  (Blackbird / XIR program I/O, state checkpoints)
 
 __version__ = "0.1.0"
 

@@ -16,7 +16,8 @@ the reference's switch to a mixed representation on single-mode preparations, SU
 ``fuse`` (lazy gate queue: ``True``/``"fold"`` default, ``"tile"``, ``False``), ``lazy_vacuum``
 (untouched modes stay product factors and gate calls are deferred until the state is observed; on by default, ``False`` applies every gate to a dense tensor as it arrives), ``device``, and for several
 GPUs ``shard`` (``True`` or a ``torch.distributed`` group: one state over all ranks, kets and
-density matrices) with ``exchange`` (``"auto"`` | ``"p2p"`` | ``"push"`` | ``"nccl"``).
+density matrices) with ``exchange`` (``"auto"`` | ``"p2p"`` | ``"push"`` | ``"nccl"``) and ``exchange_overlap``
+(how many gates behind an exchange run part by part while the rest of the shard is still in flight; 0: none).
 """
 from __future__ import annotations
 
@@ -160,7 +161,8 @@ class B200FockBackend(_Base):
                 raise NotImplementedError("sharded b200fock circuits are not batched (shard the batch instead)")
             group = None if shard is True else shard
             self.circuit = ShardedCircuit(num_subsystems, cutoff_dim, group=group, pure=pure,
-                                          exchange=kwargs.get("exchange", "auto"), **self._options)
+                                          exchange=kwargs.get("exchange", "auto"),
+                                          exchange_overlap=kwargs.get("exchange_overlap", 8), **self._options)
         else:
             self.circuit = DeviceCircuit(num_subsystems, cutoff_dim, pure, batch_size=batch_size, **self._options)
         self._modemap = ModeMap(num_subsystems)

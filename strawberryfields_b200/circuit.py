@@ -406,6 +406,18 @@ class DeviceCircuit:
         return t if t.shape[0] == nb else t.expand(nb, *t.shape[1:]).contiguous()
 
     # ------------------------------------------------------------------ raw kernels
+    # A launch may be restricted to a *view*: one index range of the OUTERMOST axis, i.e. a contiguous part
+    # of the buffer (offset, elements).  No gate acts on a sharded axis, so the parts of a shard are
+    # independent states as far as the gate kernels are concerned -- the sharded exchange uses this to run
+    # the first gates on the parts that have arrived while the rest is still in flight (sharding.py).
+    def _vptr(self):
+        view = self.__dict__.get("_view")
+        return _ptr(self._buf) if view is None else C.c_void_p(self._buf.data_ptr() + 16 * view[0])
+
+    def _vsize(self):
+        view = self.__dict__.get("_view")
+        return self._size() if view is None else view[1]
+
     def _pass(self, tag, name, *args):
         """Launch one full pass over the state.  With ``self.profile`` set to a list, the
         launch is bracketed by CUDA events on the launching stream and
@@ -418,13 +430,13 @@ class DeviceCircuit:
         e0.record()
         L.call(name, *args)
         e1.record()
-        prof.append((tag, 32 * self._B * self._size(), e0, e1))
+        prof.append((tag, 32 * self._B * self._vsize(), e0, e1))
 
     def _check_launch(self, table, per_entry, *strides):
         """Host-side bounds of a gate launch: the buffer holds B states of _size() elements, every gate
         axis lies inside one state, the table holds one entry (or B) of ``per_entry`` coefficients."""
-        size, D = self._size(), self._trunc
-        if self._buf.numel() < self._B * size:
+        size, D = self._vsize(), self._trunc
+        if self._buf.numel() < self._B * self._size():
             raise L.B200Error("state buffer holds %d elements, the launch covers %d" % (self._buf.numel(), self._B * size))
         if any(s < 1 or s * D > size for s in strides):
             raise L.B200Error("gate axis stride %r does not fit a state of %d elements" % (strides, size))
@@ -439,8 +451,8 @@ class DeviceCircuit:
         nb = U.shape[0]
         pos = self._pos[axis]
         inner = self._stride(axis)
-        self._pass("gate1/axis%d" % (naxes - 1 - pos), "b200_apply_gate1", _ptr(self._buf),
-                   self._size() // (D * inner), D, inner, _ptr(U),
+        self._pass("gate1/axis%d" % (naxes - 1 - pos), "b200_apply_gate1", self._vptr(),
+                   self._vsize() // (D * inner), D, inner, _ptr(U),
                    int(conj), B, self._size(), D * D if nb > 1 else 0, self._stream())
 
     def _k_gate2(self, G, rule, ax1, ax2, conj):
@@ -454,7 +466,7 @@ class DeviceCircuit:
         self._pass("%s/rule%d/axes%d,%d" % ("inner2" if staged else "gate2", rule, naxes - 1 - self._pos[ax1],
                                             naxes - 1 - self._pos[ax2]),
                    "b200_apply_gate2",
-                   _ptr(self._buf), self._size(), D, self._stride(ax1), self._stride(ax2),
+                   self._vptr(), self._vsize(), D, self._stride(ax1), self._stride(ax2),
                rule, _ptr(G), int(conj), B, self._size(), G.shape[1] if nb > 1 else 0, self._stream())
 
     def _k_diag_pair(self, tab, ax1, ax2, conj):
@@ -462,7 +474,7 @@ class DeviceCircuit:
         self._check_launch(tab, self._trunc ** 2, self._stride(ax1), self._stride(ax2))
         D, B = self._trunc, self._B
         nb = tab.shape[0]
-        self._pass("diag2", "b200_apply_diag", _ptr(self._buf), self._size(), D, self._stride(ax1), self._stride(ax2),
+        self._pass("diag2", "b200_apply_diag", self._vptr(), self._vsize(), D, self._stride(ax1), self._stride(ax2),
                _ptr(tab), int(conj), B, self._size(), tab.shape[1] if nb > 1 else 0, self._stream())
 
     def _k_diag_multi(self, items):
@@ -486,7 +498,7 @@ class DeviceCircuit:
             k = len(chunk)
             strides = (C.c_int64 * k)(*[s for s, _, _ in chunk])
             conjs = (C.c_int * k)(*[c for _, c, _ in chunk])
-            self._pass("diag_multi/%d" % k, "b200_apply_diag_multi", _ptr(self._buf), self._size(), D, k, strides, conjs, _ptr(tabs),
+            self._pass("diag_multi/%d" % k, "b200_apply_diag_multi", self._vptr(), self._vsize(), D, k, strides, conjs, _ptr(tabs),
                    B, self._size(), k * D if nb > 1 else 0, self._stream())
 
     # ------------------------------------------------------------------ immediate application
@@ -1010,7 +1022,8 @@ class DeviceCircuit:
             modes = [modes]
         modes = list(modes)
         if self._batched:
-            raise NotImplementedError("state preparation on a batched b200fock circuit is not supported yet")
+            self._prepare_batched(state, modes)
+            return
         self._replay()
         D, n, k = self._trunc, self._num_modes, len(modes)
         if (k == 1 and modes[0] in self._inactive and (not self._strict or not self._pure) and n > 1
@@ -1105,29 +1118,69 @@ class DeviceCircuit:
         self._scratch = None
         self._touch(*modes)
 
+    def _prepare_batched(self, state, modes):
+        """Batched circuits (TF-backend semantics, ``tfbackend/circuit.py:343-396``: one state for every batch
+        entry, or an array with a leading batch axis): single-mode KETS on modes that are still the untouched
+        vacuum -- the input encodings of a batched program.  |v> = (|v><0|) |0>, so the preparation is queued
+        as a rank-one single-mode operator (per entry when the kets differ) and costs what a gate costs.
+        Anything else would need a partial trace of every batch entry: not supported."""
+        D, B = self._trunc, self._B
+        st = np.asarray(state, dtype=C128)
+        if len(modes) != 1 or st.shape not in ((D,), (B, D)):
+            raise NotImplementedError("batched b200fock circuits prepare single-mode kets only")
+        m = modes[0]
+        log = self.__dict__.get("_defer_log")
+        if log and any(name != "_queue_dense" or args[1] == m for name, args in log):
+            self._replay()  # gates were recorded before this preparation: apply them first
+        if m not in self._untouched or m in self._pending:
+            raise NotImplementedError("batched b200fock circuits prepare states on untouched modes only")
+        kets = st.reshape(-1, D)
+        tab = np.zeros((kets.shape[0], D, D), dtype=C128)
+        tab[:, :, 0] = kets
+        table = TABLES.get(self._key("ketprep", tab.tobytes()),
+                           lambda: torch.from_numpy(tab).to(self.device))
+        if self._defer("_queue_dense", table, m):
+            return
+        self._queue_dense(table, m)
+
     def prepare(self, state, mode):
         self.prepare_multimode(state, [mode] if isinstance(mode, int) else mode)
 
     def _prepare_ket(self, ket, mode):
-        if self._pure or (mode in self._inactive and self._num_modes > 1):  # lazy vacuum: the factor is the ket
+        if self._batched:
+            self._prepare_batched(ket, [mode])
+        elif self._pure or (mode in self._inactive and self._num_modes > 1):  # lazy vacuum: the factor is the ket
             self.prepare(ket, mode)
         else:
             self.prepare(np.outer(ket, ket.conj()), mode)
 
     # single-mode kets: fockbackend/ops.py:383-461 (tiny host vectors)
+    def _kets(self, fn, *params):
+        """single-mode ket(s) from scalar parameters, or one per batch entry from length-B arrays"""
+        arrs = [np.asarray(p, dtype=np.float64) for p in params]
+        if all(a.ndim == 0 for a in arrs):
+            return fn(*[float(a) for a in arrs], self._trunc)
+        if not self._batched:
+            raise ValueError("array-valued preparation parameters need a batched circuit (batch_size=...)")
+        full = [np.broadcast_to(a, (self._B,)) for a in arrs]
+        return np.stack([fn(*[float(a[b]) for a in full], self._trunc) for b in range(self._B)])
+
     def prepare_mode_fock(self, n, mode):
-        v = np.zeros(self._trunc, dtype=C128)
-        v[n] = 1.0
-        self._prepare_ket(v, mode)
+        def fock(k, D):
+            v = np.zeros(D, dtype=C128)
+            v[int(k)] = 1.0
+            return v
+
+        self._prepare_ket(self._kets(fock, n), mode)
 
     def prepare_mode_coherent(self, r, phi, mode):
-        self._prepare_ket(_coherent(r, phi, self._trunc), mode)
+        self._prepare_ket(self._kets(_coherent, r, phi), mode)
 
     def prepare_mode_squeezed(self, r, theta, mode):
-        self._prepare_ket(_squeezed(r, theta, self._trunc), mode)
+        self._prepare_ket(self._kets(_squeezed, r, theta), mode)
 
     def prepare_mode_displaced_squeezed(self, r_d, phi_d, r_s, phi_s, mode):
-        self._prepare_ket(_displaced_squeezed(r_d, phi_d, r_s, phi_s, self._trunc), mode)
+        self._prepare_ket(self._kets(_displaced_squeezed, r_d, phi_d, r_s, phi_s), mode)
 
     def prepare_mode_thermal(self, nbar, mode):
         D = self._trunc
@@ -1333,9 +1386,60 @@ class DeviceCircuit:
             return np.random.choice(list(range(len(dist))), p=dist / sum(dist))
         return np.random.choice(list(range(len(dist))), p=dist)
 
+    def _measure_fock_batched(self, modes, select):
+        """Batched ``measure_fock`` (TF-backend semantics, ``tfbackend/circuit.py:612-760``): every batch entry
+        is measured on its own -- ``select`` is one list for all entries or an array ``[B, len(modes)]`` --
+        and the result has shape ``[B, len(modes)]``.  The marginals of all entries come from ONE device
+        reduction; the draws are numpy's, entry by entry in batch order (one uniform each, as in the
+        unbatched path); projection and renormalisation are launched per entry (the outcomes differ)."""
+        D, B, k = self._trunc, self._B, len(modes)
+        self._flush()
+        self._canonicalize()
+        if select is not None:
+            sel = np.asarray(select)
+            if np.any(sel == None):  # noqa: E711
+                raise NotImplementedError("Post-selection lists must only contain numerical values.")
+            if sel.shape == (k,):
+                sel = np.vstack([sel] * B)
+            if sel.shape != (B, k):
+                raise ValueError("The shape of 'select' is incompatible with 'modes'.")
+            outcomes = sel.astype(np.int64)
+        else:
+            keep = sorted(modes)
+            dist_all = self.marginal_probs_device(keep).cpu().numpy()
+            order = np.argsort(modes)
+            outcomes = np.zeros((B, k), dtype=np.int64)
+            for b in range(B):
+                dist = dist_all[b] * ~np.isclose(dist_all[b], 0.0)
+                i = self._sample_index(dist)
+                digits = [i // D ** (k - 1 - j) % D for j in range(k)]
+                for j in range(k):
+                    outcomes[b, order[j]] = int(digits[j])
+        # |0..0><outcome| on every entry: out of place into one zeroed buffer, one strided copy per entry
+        per = self._size()
+        out = self._get_scratch(self._buf.numel())
+        L.call("b200_fill_zero", _ptr(out), out.numel(), self._stream())
+        oa = [(D, self._stride(ax), 0, self._stride(ax)) for m in range(self._num_modes) if m not in modes
+              for ax in self._mode_axes(m)]
+        for b in range(B):
+            base_a = b * per + sum(int(v) * self._stride(ax) for m, v in zip(modes, outcomes[b]) for ax in self._mode_axes(m))
+            self._gather(self._buf, None, out, oa, base=(base_a, 0, b * per))
+        if self._shared:
+            self._buf, self._scratch, self._shared = out, None, False
+        else:
+            self._buf, self._scratch = out, self._buf
+        nrm = self._norm_device(materialize=False)
+        if bool((nrm == 0).any().item()):
+            raise ZeroDivisionError("Measurement has zero probability.")
+        for b in range(B):
+            L.call("b200_scale", C.c_void_p(self._buf.data_ptr() + 16 * b * per), per, 1.0, 0.0,
+                   C.c_void_p(nrm.data_ptr() + 8 * b), 1 if self._pure else 0, self._stream())
+        self._touch(*modes)
+        return outcomes
+
     def measure_fock(self, modes, select=None):
         if self._batched:
-            raise NotImplementedError("measure_fock on a batched b200fock circuit is not supported yet")
+            return self._measure_fock_batched(list(modes), select)
         if select is not None and np.any(np.array(select) == None):  # noqa: E711
             raise NotImplementedError("Post-selection lists must only contain numerical values.")
         self._flush()

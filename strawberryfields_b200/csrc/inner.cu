@@ -10,9 +10,10 @@
 //     mbarrier) and a storer (shared -> global, bulk groups), the handful of copies of a tile dealt to
 //     their lanes: full-sector requests, no per-element address arithmetic, and the write-back is
 //     asynchronous too;
-//   * ten consumer warps run the same register-blocked tasks as the streaming kernel on the staged
-//     tile, in place (different tasks of a slice touch disjoint elements), and hand the stage on
-//     through mbarriers -- there is no __syncthreads in the steady state;
+//   * teams of ten consumer warps (two teams on alternate tiles for cutoffs up to 12) run the same
+//     register-blocked tasks as the streaming kernel on the staged tile, in place (different tasks of a
+//     slice touch disjoint elements), and hand the stage on through mbarriers -- there is no
+//     __syncthreads in the steady state;
 //   * a CTA per SM walks a contiguous range of tiles with a ring of 3-4 stages, so 2-3 tiles
 //     (100-150 KB per SM) are in flight while one is being computed: the FP64 work (~1400 of the
 //     ~3500 cycles a tile's bytes take at the HBM rate) is off the critical path;
@@ -38,8 +39,12 @@
 
 namespace b200 {
 
-constexpr int IN_CONSUMERS = 10;                       // consumer warps
-constexpr int IN_THREADS = 32 * (IN_CONSUMERS + 2);    // + a loader and a storer warp
+constexpr int IN_TEAM = 10;                            // consumer warps that share one tile
+// Two teams work on alternate tiles when the register file allows (cutoffs up to 12): twenty warps keep
+// the FP64 pipe fed through the dependent-issue latency of the DFMA chains (ncu, one team: "wait" was the
+// top stall and the pipe 31 % busy; the dense one-mode task was compute-latency bound at 3.8 TB/s).
+__host__ __device__ constexpr int in_teams(int D) { return D <= 12 ? 2 : 1; }
+__host__ __device__ constexpr int in_threads(int teams) { return 32 * (IN_TEAM * teams + 2); }  // + loader, storer
 constexpr int IN_MAX_STAGES = 4;
 constexpr int IN_COPY_MAX = 16 * 1024;                 // bytes per bulk copy
 constexpr int IN_SMEM_LIMIT = 227 * 1024 - 1024;       // dynamic shared memory budget
@@ -54,6 +59,8 @@ struct InnerPlan {
   //                                     + s / gran   (one pad word per granule of `gran` slices; gran = 0: none)
   int block_slices, block_elems, row_ss;
   int gran, r;              // padding granule (slices) and r = 8 / gcd(row_ss mod 8, 8) of the lane map
+  int wide;                 // 1: granules of 32 slices, the lane map spreads a warp over 8/r of them
+  int teams;                // consumer teams launched (1 or 2, at most in_teams(D))
   int sk, sl;               // staged element strides of gate index 1 / 2 inside a slice
   int rows, row_pitch;      // rows mode: D rows, staged row pitch in elements
   int chunks_per_outer;     // rows mode: ceil(mid / slices_per_tile)
@@ -123,8 +130,11 @@ __device__ __forceinline__ void tile_copy(const InnerPlan& p, const Geometry& g,
   }
 }
 
-template <int D>
-__global__ void __launch_bounds__(IN_THREADS, 1)
+// TEAMS is a template parameter because it sets the register budget: one team (384 threads) compiles to
+// ~133 registers, two teams (704 threads) are capped at 80 -- running one team under the 80-register cap
+// cost the pair-gate kernel a quarter of its rate (4.6 against 5.8-6.1 TB/s).
+template <int D, int TEAMS>
+__global__ void __launch_bounds__(in_threads(TEAMS), 1)
 k_apply_inner_tma(cplx* __restrict__ state, const cplx* __restrict__ coef, const Geometry g, const TaskTable tt,
                   const InnerPlan p, unsigned long long n_tiles /* over all batch entries */) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -135,7 +145,7 @@ k_apply_inner_tma(cplx* __restrict__ state, const cplx* __restrict__ coef, const
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
-      mbar_init(smem_u32(&done_bar[s]), IN_CONSUMERS);
+      mbar_init(smem_u32(&done_bar[s]), IN_TEAM);
       mbar_init(smem_u32(&free_bar[s]), 1);
     }
     mbar_fence_init();
@@ -150,7 +160,7 @@ k_apply_inner_tma(cplx* __restrict__ state, const cplx* __restrict__ coef, const
   const unsigned long long n_my = t_hi - t_lo;
   const unsigned S = (unsigned)p.stages;
 
-  if (warp >= IN_CONSUMERS) {
+  if (warp >= IN_TEAM * TEAMS) {
     // ---------------- DMA warps: a loader and a storer, their 32 lanes share a tile's copies ---------
     auto where = [&](unsigned long long i, cplx*& base, unsigned long long& t) {
       const unsigned long long gt = t_lo + i;
@@ -160,7 +170,7 @@ k_apply_inner_tma(cplx* __restrict__ state, const cplx* __restrict__ coef, const
     };
     cplx* base;
     unsigned long long t;
-    if (warp == IN_CONSUMERS) {
+    if (warp == IN_TEAM * TEAMS) {
       for (unsigned long long i = 0; i < n_my; ++i) {
         const unsigned st = (unsigned)(i % S);
         if (i >= S) mbar_wait(smem_u32(&free_bar[st]), (unsigned)(((i / S) - 1) & 1));  // tile i-S has left the stage
@@ -186,45 +196,52 @@ k_apply_inner_tma(cplx* __restrict__ state, const cplx* __restrict__ coef, const
     return;
   }
 
-  // ---------------- consumer warps ------------------------------------------------------------
+  // ---------------- consumer warps: team `team` takes the tiles i = team, team + TEAMS, ... ----------
+  const int team = warp / IN_TEAM, wteam = warp - team * IN_TEAM;
+  cplx* Mt = M + (size_t)team * g.coef_count;   // every team keeps its own copy of the gate table
   const long long step = p.sk + tt.dl * p.sl;
   const int n_wt = p.groups * tt.ntasks;
   // conflict-free lane -> slice map inside a group of 32 slices (identity when no padding is needed)
+  // gran = 4r: lane l of a group takes slice 4r * (x mod w) + x / w + r * (l / 8), x = l mod 8, w = 8 / r.
+  // wide (gran = 32, one-mode gates: fewer, larger bulk copies): w consecutive groups form a super-group;
+  // its h-th warp-task takes, from granule (x mod w), slice 4r * h + x / w + r * (l / 8).
   int lane_slice = lane;
+  const int lw = p.gran > 0 ? 8 / p.r : 1;
   if (p.gran > 0) {
-    const int x = lane & 7, w = 8 / p.r;
-    lane_slice = 4 * p.r * (x % w) + x / w + p.r * (lane >> 3);
+    const int x = lane & 7;
+    lane_slice = p.wide ? 32 * (x % lw) + x / lw + p.r * (lane >> 3)
+                        : 4 * p.r * (x % lw) + x / lw + p.r * (lane >> 3);
   }
   long long cur_batch = -1;
-  for (unsigned long long i = 0; i < n_my; ++i) {
+  for (unsigned long long i = team; i < n_my; i += TEAMS) {
     const unsigned long long gt = t_lo + i;
     const long long b = (long long)(gt / p.tiles_per_state);
     const unsigned long long t = gt - (unsigned long long)b * p.tiles_per_state;
     if (b != cur_batch && (cur_batch < 0 || g.coef_batch_stride != 0)) {
-      // (re)load the gate table: every consumer has finished the previous batch entry's tiles
-      asm volatile("bar.sync 1, %0;\n" ::"n"(IN_CONSUMERS * 32) : "memory");
+      // (re)load the team's gate table: the whole team has finished the previous batch entry's tiles
+      asm volatile("bar.sync %0, %1;\n" ::"r"(1 + team), "n"(IN_TEAM * 32) : "memory");
       const cplx* cg = coef + (size_t)b * g.coef_batch_stride;
-      for (int e = threadIdx.x; e < g.coef_count; e += IN_CONSUMERS * 32) {
+      for (int e = wteam * 32 + lane; e < g.coef_count; e += IN_TEAM * 32) {
         cplx v = cg[e];
         if (g.conj) v.y = -v.y;
-        M[e] = v;
+        Mt[e] = v;
       }
-      asm volatile("bar.sync 1, %0;\n" ::"n"(IN_CONSUMERS * 32) : "memory");
+      asm volatile("bar.sync %0, %1;\n" ::"r"(1 + team), "n"(IN_TEAM * 32) : "memory");
     }
     cur_batch = b;
     const unsigned st = (unsigned)(i % S);
     mbar_wait(smem_u32(&full_bar[st]), (unsigned)((i / S) & 1));
     cplx* tile = tiles + (size_t)st * p.tile_elems;
     const int nsl = tile_slices(p, g, t);
-    for (int wt = warp; wt < n_wt; wt += IN_CONSUMERS) {
+    for (int wt = wteam; wt < n_wt; wt += IN_TEAM) {
       const int gi = wt / tt.ntasks, task = wt - gi * tt.ntasks;
-      const int sg = gi * 32 + lane_slice;
+      const int sg = p.wide ? (gi / lw) * lw * 32 + 4 * p.r * (gi % lw) + lane_slice : gi * 32 + lane_slice;
       if (sg < nsl) {
         cplx* ps = tile + (sg / p.block_slices) * p.block_elems + (sg % p.block_slices) * p.row_ss +
                    (p.gran > 0 ? sg / p.gran : 0);
         const SubBlock sb0 = tt.sub[task][0], sb1 = tt.sub[task][1];
         task_dispatch<D>(sb0.c, ps + sb0.start_k * p.sk + sb0.start_l * p.sl,
-                         ps + sb1.start_k * p.sk + sb1.start_l * p.sl, step, M + sb0.coef, M + sb1.coef);
+                         ps + sb1.start_k * p.sk + sb1.start_l * p.sl, step, Mt + sb0.coef, Mt + sb1.coef);
       }
     }
     fence_async_smem();  // generic-proxy writes to the stage become visible to the bulk store
@@ -233,20 +250,30 @@ k_apply_inner_tma(cplx* __restrict__ state, const cplx* __restrict__ coef, const
   }
 }
 
-template <int D>
-static cudaError_t launch_d(cplx* state, const cplx* coef, const Geometry& g, const TaskTable& tt,
-                            const InnerPlan& p, unsigned long long n_tiles, size_t smem, cudaStream_t st) {
+template <int D, int TEAMS>
+static cudaError_t launch_dt(cplx* state, const cplx* coef, const Geometry& g, const TaskTable& tt,
+                             const InnerPlan& p, unsigned long long n_tiles, size_t smem, cudaStream_t st) {
   static int sms = 0;
   if (sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
   }
-  cudaError_t e = cudaFuncSetAttribute(k_apply_inner_tma<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e =
+      cudaFuncSetAttribute(k_apply_inner_tma<D, TEAMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const unsigned grid = (unsigned)(n_tiles < (unsigned long long)sms ? n_tiles : (unsigned long long)sms);
-  k_apply_inner_tma<D><<<grid, IN_THREADS, smem, st>>>(state, coef, g, tt, p, n_tiles);
+  k_apply_inner_tma<D, TEAMS><<<grid, in_threads(TEAMS), smem, st>>>(state, coef, g, tt, p, n_tiles);
   return cudaSuccess;
+}
+
+template <int D>
+static cudaError_t launch_d(cplx* state, const cplx* coef, const Geometry& g, const TaskTable& tt,
+                            const InnerPlan& p, unsigned long long n_tiles, size_t smem, cudaStream_t st) {
+  if constexpr (in_teams(D) == 2) {
+    if (p.teams == 2) return launch_dt<D, 2>(state, coef, g, tt, p, n_tiles, smem, st);
+  }
+  return launch_dt<D, 1>(state, coef, g, tt, p, n_tiles, smem, st);
 }
 
 static int gcd_int(int a, int b) { return b == 0 ? a : gcd_int(b, a % b); }
@@ -273,6 +300,20 @@ bool launch_inner_tma(int D, cplx* state, const cplx* coef, const Geometry& g, c
     p.block_elems = 0;
     p.row_ss = D;
     pad_plan(D);
+    // wide granules (32 slices per bulk copy instead of 4r) when the groups of a tile pair up; B200_INNER_ONE
+    // = "narrow" / "flat" select the 4r granules / the unpadded layout (measurement switches)
+    // Measured (B200, D = 10, profiles/r02_inner_kernel.md): the one-mode tile is ONE contiguous 51 KB run, and
+    // every extra bulk copy costs more than the bank conflicts it removes -- unpadded ("flat", 4 copies of
+    // <= 16 KB, 2-way conflicts) 5.2 TB/s, granules of 32 slices ("wide", 10 copies) 4.4, of 4r ("narrow", 20
+    // copies) 3.7.  B200_INNER_ONE = wide / narrow select the padded layouts.
+    static const char* one_mode = getenv("B200_INNER_ONE");
+    if (one_mode && one_mode[0] == 'w' && p.gran > 0 && p.groups % (8 / p.r) == 0) {
+      p.wide = 1;
+      p.gran = 32;
+    } else if (!(one_mode && one_mode[0] == 'n')) {
+      p.gran = 0;
+      p.r = 8;
+    }
     p.sk = 1;
     p.sl = 0;
     p.tile_elems = p.slices_per_tile * D + (p.gran ? p.slices_per_tile / p.gran : 0);
@@ -285,12 +326,23 @@ bool launch_inner_tma(int D, cplx* state, const cplx* coef, const Geometry& g, c
     if (mid >= 32u * (unsigned)q) {
       p.rows_mode = 1;
       p.groups = q;
-      p.slices_per_tile = 32 * q;
+      // a row run of `mid` slices is cut into equal chunks of at most 32 * q slices (mid = 100: 4 x 25, not
+      // 3 x 32 + 4)
+      p.chunks_per_outer = (int)((mid + 32u * q - 1) / (32u * q));
+      p.slices_per_tile = (int)((mid + p.chunks_per_outer - 1) / p.chunks_per_outer);
       p.rows = D;
       p.row_ss = D;
-      pad_plan(D);
+      // Measured (tools/inner_probe.py, D = 10): padding the rows (two granules of 16 slices per row, 20 + 20
+      // bulk copies per tile) gives 3.5 TB/s, unpadded rows (10 + 10 copies, 2-way bank conflicts) 4.8 TB/s:
+      // rows stay unpadded.  B200_INNER_ROWS=pad selects the padded layout.
+      static const char* rows_mode = getenv("B200_INNER_ROWS");
+      if (rows_mode && rows_mode[0] == 'p' && p.slices_per_tile % 32 == 0) {
+        pad_plan(D);
+      } else {
+        p.gran = 0;
+        p.r = 8;
+      }
       p.row_pitch = p.slices_per_tile * D + (p.gran ? p.slices_per_tile / p.gran : 0);
-      p.chunks_per_outer = (int)((mid + p.slices_per_tile - 1) / p.slices_per_tile);
       p.hi_stride = hi;
       p.block_slices = p.slices_per_tile;
       p.block_elems = 0;
@@ -325,9 +377,16 @@ bool launch_inner_tma(int D, cplx* state, const cplx* coef, const Geometry& g, c
     p.sk = g.stride1 > g.stride2 ? hi_staged : 1;
     p.sl = g.stride1 > g.stride2 ? 1 : hi_staged;
   }
+  // Two consumer teams for the dense one-mode task (400 DFMA per warp-task: one team was compute-latency
+  // bound, 3.7-4.9 TB/s); one team for pair gates, where a second team would take the ring stage that keeps
+  // a second tile of loads in flight (measured 5.2-5.5 against 5.8-6.1 TB/s).  B200_INNER_TEAMS overrides.
+  static const char* teams_env = getenv("B200_INNER_TEAMS");
+  p.teams = pair ? 1 : 2;
+  if (teams_env && (teams_env[0] == '1' || teams_env[0] == '2')) p.teams = teams_env[0] - '0';
+  if (p.teams > in_teams(D)) p.teams = in_teams(D);
   const size_t tile_bytes = (((size_t)p.tile_elems * 16) + 127) / 128 * 128;
   p.tile_elems = (int)(tile_bytes / 16);
-  const size_t coef_bytes = (size_t)g.coef_count * 16;
+  const size_t coef_bytes = (size_t)g.coef_count * 16 * p.teams;  // one copy of the table per team
   if (coef_bytes + 3 * tile_bytes > (size_t)IN_SMEM_LIMIT) return false;  // fewer than three stages: not worth it
   p.stages = (int)((IN_SMEM_LIMIT - coef_bytes) / tile_bytes);
   if (p.stages > IN_MAX_STAGES) p.stages = IN_MAX_STAGES;

@@ -1,0 +1,647 @@
+"""Program I/O for ``b200fock``: Blackbird (``.xbb``) and XIR (``.xir``) scripts in and out,
+and an on-disk checkpoint of the simulated state -- without the ``blackbird`` / ``xir`` packages.
+
+The reference loads stored programs with ``sf.load`` / ``sf.loads`` and writes them with ``sf.save``
+(``/root/reference/strawberryfields/io/__init__.py:67,145,169``), going through the third-party parsers
+``blackbird`` and ``xir`` (``io/blackbird_io.py:30,164``, ``io/xir_io.py:64,218``).  Neither is in this
+image, and the GPU box has no Strawberry Fields either, so this module carries its own small parsers for
+the parts of both languages a Fock-backend program uses:
+
+* Blackbird: ``name`` / ``version`` / ``target dev (opt = val)`` header, scalar and array variable
+  declarations (``float x = 0.3``, ``complex array U[4, 4] =`` + indented rows), comments, and operation
+  lines ``Op(args, key=val) | modes``.  ``for`` loops, templates (``{par}``) and measured parameters
+  (``q0``) are refused with ``NotImplementedError``.
+* XIR: ``options: .. end;`` and ``constants: .. end;`` blocks, ``use`` / declaration statements (ignored),
+  and statements ``Op(args, key: val) | [wires];``.
+
+A loaded script is a :class:`CircuitProgram`: the list of operations in the form the reference's
+converters consume (``{"op", "args", "kwargs", "modes"}``, ``blackbird_io.py:46-75``).  ``calls()`` lowers
+it to ``BaseFock`` backend calls -- what ``LocalEngine._run_program`` makes after the ``fock`` compiler has
+decomposed the program (``engine.py:422-457``): primitive gates map one to one; ``Xgate``, ``Zgate``,
+``Pgate``, ``CXgate``, ``CZgate``, ``Fouriergate`` use the reference's decompositions
+(``ops.py:1726-1732,2149-2158,2209-2216``) and ``Interferometer(U)`` the rectangular (Clements) mesh in the
+reference's gate order (``ops.py:2655-2718``).  ``run(backend)`` executes it and returns the measurement
+samples; ``to_sf()`` builds a ``strawberryfields.Program`` when Strawberry Fields is importable.
+
+State checkpoints (``save_state`` / ``load_state``) are ``.npz`` files with the ket or density matrix in
+the reference's layout (``backend.py:50-56``) plus cutoff, purity and mode count; a state object of a
+sharded circuit gathers its shards first (checkpoints of states that do not fit one host are written per
+rank by ``ShardedCircuit.save_shard`` / ``load_shard``).
+"""
+from __future__ import annotations
+
+import ast
+import math
+import os
+import re
+
+import numpy as np
+
+HBAR = 2.0  # strawberryfields.hbar default; Xgate / Zgate displacements are x / sqrt(2 hbar)
+
+_FUNCS = {
+    "sqrt": np.sqrt, "sin": np.sin, "cos": np.cos, "tan": np.tan, "exp": np.exp, "log": np.log,
+    "arcsin": np.arcsin, "arccos": np.arccos, "arctan": np.arctan, "arctan2": np.arctan2,
+    "asin": np.arcsin, "acos": np.arccos, "atan": np.arctan, "sinh": np.sinh, "cosh": np.cosh,
+    "tanh": np.tanh, "arcsinh": np.arcsinh, "arccosh": np.arccosh, "arctanh": np.arctanh, "abs": abs,
+}
+_CONSTS = {"pi": math.pi, "PI": math.pi, "e": math.e, "True": True, "False": False, "true": True, "false": False,
+           "None": None, "none": None}
+
+
+class ProgramSyntaxError(ValueError):
+    """A script that is not valid Blackbird / XIR (``blackbird.BlackbirdSyntaxError`` in the reference)."""
+
+
+def _eval(expr, env):
+    """Evaluate a Blackbird / XIR parameter expression: numbers (``1+2j`` included), declared variables,
+    ``pi``, arithmetic and the usual real functions.  Anything else is refused (no ``eval``)."""
+    expr = expr.strip()
+    if not expr:
+        raise ProgramSyntaxError("empty expression")
+    if re.fullmatch(r"q\d+", expr):
+        raise NotImplementedError("measured parameters (%s) are not supported by the b200fock loader" % expr)
+    try:
+        tree = ast.parse(expr, mode="eval")
+    except SyntaxError as exc:
+        raise ProgramSyntaxError("cannot parse expression %r" % expr) from exc
+
+    def ev(node):
+        if isinstance(node, ast.Expression):
+            return ev(node.body)
+        if isinstance(node, ast.Constant):
+            if isinstance(node.value, (int, float, complex, bool, str)) or node.value is None:
+                return node.value
+        elif isinstance(node, ast.Name):
+            if node.id in env:
+                return env[node.id]
+            if node.id in _CONSTS:
+                return _CONSTS[node.id]
+            if re.fullmatch(r"q\d+", node.id):
+                raise NotImplementedError("measured parameters (%s) are not supported by the b200fock loader" % node.id)
+            raise NameError("name %r is not defined in the script" % node.id)
+        elif isinstance(node, ast.UnaryOp) and isinstance(node.op, (ast.USub, ast.UAdd)):
+            v = ev(node.operand)
+            return -v if isinstance(node.op, ast.USub) else v
+        elif isinstance(node, ast.BinOp):
+            a, b = ev(node.left), ev(node.right)
+            if isinstance(node.op, ast.Add):
+                return a + b
+            if isinstance(node.op, ast.Sub):
+                return a - b
+            if isinstance(node.op, ast.Mult):
+                return a * b
+            if isinstance(node.op, ast.Div):
+                return a / b
+            if isinstance(node.op, ast.Pow):
+                return a ** b
+        elif isinstance(node, ast.Call) and isinstance(node.func, ast.Name) and node.func.id in _FUNCS \
+                and not node.keywords:
+            return _FUNCS[node.func.id](*[ev(a) for a in node.args])
+        elif isinstance(node, (ast.List, ast.Tuple)):
+            return [ev(e) for e in node.elts]
+        elif isinstance(node, ast.Subscript) and isinstance(node.value, ast.Name) and node.value.id in env:
+            idx = ev(node.slice)
+            return np.asarray(env[node.value.id])[tuple(idx) if isinstance(idx, list) else idx]
+        raise ProgramSyntaxError("unsupported expression %r" % expr)
+
+    return ev(tree)
+
+
+def _split_top(text, sep=","):
+    """split at ``sep`` outside brackets / parentheses"""
+    out, depth, cur = [], 0, []
+    for ch in text:
+        if ch in "([{":
+            depth += 1
+        elif ch in ")]}":
+            depth -= 1
+        if ch == sep and depth == 0:
+            out.append("".join(cur))
+            cur = []
+        else:
+            cur.append(ch)
+    if "".join(cur).strip():
+        out.append("".join(cur))
+    return out
+
+
+def _parse_args(text, env, kw_sep):
+    args, kwargs = [], {}
+    for item in _split_top(text):
+        item = item.strip()
+        m = re.match(r"^([A-Za-z_]\w*)\s*%s(?!=)\s*(.+)$" % re.escape(kw_sep), item, re.S)
+        if m:
+            kwargs[m.group(1)] = _eval(m.group(2), env)
+        else:
+            if kwargs:
+                raise ProgramSyntaxError("positional argument after a keyword argument: %r" % item)
+            args.append(_eval(item, env))
+    return args, kwargs
+
+
+def _parse_modes(text):
+    text = text.strip()
+    if text and text[0] in "[(":
+        if text[-1] not in "])":
+            raise ProgramSyntaxError("unbalanced mode list %r" % text)
+        text = text[1:-1]
+    modes = []
+    for tok in text.split(","):
+        tok = tok.strip()
+        if not tok:
+            continue
+        if not re.fullmatch(r"\d+", tok):
+            raise ProgramSyntaxError("mode index %r is not an integer" % tok)
+        modes.append(int(tok))
+    if not modes:
+        raise ProgramSyntaxError("an operation needs at least one mode")
+    return modes
+
+
+_OP_LINE = re.compile(r"^([A-Za-z_]\w*)\s*(?:\((.*)\))?\s*\|\s*(.+)$", re.S)
+
+
+class CircuitProgram:
+    """A loaded circuit: header fields and the operation list (``{"op", "args", "kwargs", "modes"}``)."""
+
+    def __init__(self, name=None, version="1.0", target=None, operations=None, options=None):
+        self.name = name
+        self.version = version
+        self.target = target or {"name": None, "options": {}}
+        self.operations = list(operations or [])
+        self.options = dict(options or {})     # XIR options (cutoff_dim, shots, ..)
+
+    @property
+    def num_subsystems(self):
+        return 1 + max((m for op in self.operations for m in op["modes"]), default=-1)
+
+    @property
+    def run_options(self):
+        opts = dict(self.target.get("options", {}))
+        return {k: opts[k] for k in ("shots",) if k in opts} | {k: self.options[k] for k in ("shots",) if k in self.options}
+
+    @property
+    def backend_options(self):
+        return {k: self.options[k] for k in ("cutoff_dim",) if k in self.options}
+
+    # ------------------------------------------------------------------ lowering to backend calls
+    def calls(self):
+        """``[(method, *args)]``: the ``BaseFock`` calls of the program (measurements included, in place)."""
+        out = []
+        for op in self.operations:
+            out.extend(lower(op["op"], op.get("args", []), op.get("kwargs", {}), op["modes"]))
+        return out
+
+    def run(self, backend, cutoff_dim=None, **begin_options):
+        """``begin_circuit`` + every call; returns ``{mode: [outcomes]}`` like ``Result.samples_dict``."""
+        D = cutoff_dim if cutoff_dim is not None else self.backend_options.get("cutoff_dim")
+        if D is None:
+            raise ValueError("Argument 'cutoff_dim' must be passed to the Fock backend")
+        backend.begin_circuit(self.num_subsystems, cutoff_dim=int(D), **begin_options)
+        samples = {}
+        for call in self.calls():
+            ret = getattr(backend, call[0])(*call[1:-1], **call[-1]) if isinstance(call[-1], dict) else \
+                getattr(backend, call[0])(*call[1:])
+            if call[0].startswith("measure_"):
+                modes = call[2] if call[0] == "measure_homodyne" else call[1]
+                modes = [modes] if isinstance(modes, int) else list(modes)
+                vals = np.asarray(ret).reshape(-1)
+                for m, v in zip(modes, vals):
+                    samples.setdefault(m, []).append(v.item() if hasattr(v, "item") else v)
+        return samples
+
+    def to_sf(self):
+        """The same program as a ``strawberryfields.Program`` (needs Strawberry Fields)."""
+        import strawberryfields as sf
+        from strawberryfields import ops
+
+        prog = sf.Program(self.num_subsystems, name=self.name)
+        with prog.context as q:
+            for op in self.operations:
+                if op["op"] not in ops.__all__:
+                    raise NameError("Quantum operation {} not defined!".format(op["op"]))
+                gate = getattr(ops, op["op"])
+                regs = [q[i] for i in op["modes"]]
+                if op.get("args") or op.get("kwargs"):
+                    gate(*op.get("args", []), **op.get("kwargs", {})) | regs  # noqa: pylint: disable=expression-not-assigned
+                else:
+                    (gate() if isinstance(gate, type) else gate) | regs  # noqa
+        prog.run_options.update(self.run_options)
+        prog.backend_options.update(self.backend_options)
+        return prog
+
+    # ------------------------------------------------------------------ serialisation
+    def serialize(self, ir="blackbird"):
+        return dumps(self, ir)
+
+
+# ---------------------------------------------------------------------------------------- Blackbird
+_TYPES = ("int", "float", "complex", "str", "bool")
+
+
+def _loads_blackbird(text):
+    if re.search(r"\{\s*[A-Za-z_]\w*\s*\}", text):
+        raise NotImplementedError("Blackbird templates ({parameter}) are not supported by the b200fock loader")
+    prog = CircuitProgram()
+    env = {}
+    lines = text.splitlines()
+    i = 0
+
+    def strip(line):
+        return line.split("#", 1)[0].rstrip()
+
+    while i < len(lines):
+        line = strip(lines[i])
+        i += 1
+        s = line.strip()
+        if not s:
+            continue
+        head = s.split(None, 1)
+        if head[0] == "name":
+            prog.name = head[1].strip() if len(head) > 1 else None
+            if prog.name == "None":
+                prog.name = None
+        elif head[0] == "version":
+            prog.version = head[1].strip() if len(head) > 1 else "1.0"
+        elif head[0] == "target":
+            m = re.match(r"^target\s+([\w.\-]+)\s*(?:\((.*)\))?\s*$", s)
+            if not m:
+                raise ProgramSyntaxError("bad target line: %r" % s)
+            opts = {}
+            if m.group(2):
+                _, opts = _parse_args(m.group(2), env, "=")
+            prog.target = {"name": m.group(1), "options": opts}
+        elif head[0] in ("for", "type", "include"):
+            raise NotImplementedError("Blackbird %r statements are not supported by the b200fock loader" % head[0])
+        elif head[0] in _TYPES and len(head) > 1 and "=" in s and "|" not in s.split("=", 1)[0]:
+            rest = head[1]
+            if rest.startswith("array"):
+                m = re.match(r"^array\s+([A-Za-z_]\w*)\s*(?:\[([^\]]*)\])?\s*=\s*(.*)$", rest)
+                if not m:
+                    raise ProgramSyntaxError("bad array declaration: %r" % s)
+                rows = []
+                if m.group(3).strip():
+                    rows.append(m.group(3))
+                while i < len(lines) and (lines[i].startswith((" ", "\t")) and strip(lines[i]).strip()):
+                    rows.append(strip(lines[i]).strip())
+                    i += 1
+                data = [[_eval(x, env) for x in _split_top(r) if x.strip()] for r in rows]
+                arr = np.array(data, dtype={"int": int, "float": float, "complex": complex}.get(head[0], object))
+                if m.group(2):
+                    shape = [int(_eval(x, env)) for x in m.group(2).split(",") if x.strip()]
+                    if list(arr.shape) != shape and arr.size == int(np.prod(shape)):
+                        arr = arr.reshape(shape)
+                    if list(arr.shape) != shape:
+                        raise ProgramSyntaxError("array %s has shape %r, declared %r" % (m.group(1), arr.shape, shape))
+                env[m.group(1)] = arr
+            else:
+                m = re.match(r"^([A-Za-z_]\w*)\s*=\s*(.+)$", rest)
+                if not m:
+                    raise ProgramSyntaxError("bad variable declaration: %r" % s)
+                val = _eval(m.group(2), env)
+                env[m.group(1)] = {"int": int, "float": float, "complex": complex, "str": str, "bool": bool}[head[0]](val)
+        else:
+            m = _OP_LINE.match(s)
+            if not m:
+                raise ProgramSyntaxError("cannot parse line %d: %r" % (i, s))
+            args, kwargs = _parse_args(m.group(2), env, "=") if m.group(2) and m.group(2).strip() else ([], {})
+            prog.operations.append({"op": m.group(1), "args": args, "kwargs": kwargs, "modes": _parse_modes(m.group(3))})
+    return prog
+
+
+def _fmt(v):
+    if isinstance(v, np.ndarray):
+        return "[" + ", ".join(_fmt(x) for x in v) + "]"
+    if isinstance(v, (list, tuple)):
+        return "[" + ", ".join(_fmt(x) for x in v) + "]"
+    if isinstance(v, (complex, np.complexfloating)):
+        return "%r%s%rj" % (float(v.real), "+" if v.imag >= 0 else "-", abs(float(v.imag)))
+    if isinstance(v, (bool, np.bool_)) or v is None:
+        return str(v)
+    if isinstance(v, (int, np.integer)):
+        return str(int(v))
+    if isinstance(v, (float, np.floating)):
+        return repr(float(v))
+    return str(v)
+
+
+def _dumps_blackbird(prog):
+    out = ["name %s" % prog.name, "version %s" % (prog.version or "1.0")]
+    if prog.target.get("name"):
+        opts = ", ".join("%s=%s" % (k, _fmt(v)) for k, v in prog.target.get("options", {}).items())
+        out.append("target %s%s" % (prog.target["name"], " (%s)" % opts if opts else ""))
+    out.append("")
+    arrays = 0
+    body = []
+    for op in prog.operations:
+        parts = []
+        for a in op.get("args", []):
+            if isinstance(a, np.ndarray) and a.ndim == 2:
+                name = "A%d" % arrays
+                arrays += 1
+                kind = "complex" if np.iscomplexobj(a) else "float"
+                out.append("%s array %s[%d, %d] =" % (kind, name, a.shape[0], a.shape[1]))
+                out.extend("    " + ", ".join(_fmt(x) for x in row) for row in a)
+                out.append("")
+                parts.append(name)
+            else:
+                parts.append(_fmt(a))
+        parts += ["%s=%s" % (k, _fmt(v)) for k, v in op.get("kwargs", {}).items()]
+        modes = op["modes"]
+        body.append("%s(%s) | %s" % (op["op"], ", ".join(parts), modes[0] if len(modes) == 1 else "[%s]" % ", ".join(map(str, modes))))
+    return "\n".join(out + body) + "\n"
+
+
+# ---------------------------------------------------------------------------------------------- XIR
+def _loads_xir(text):
+    text = re.sub(r"//[^\n]*", "", text)
+    prog = CircuitProgram(version="0.1.0")
+    env = {}
+    for kind in ("options", "constants"):
+        m = re.search(r"\b%s\s*:(.*?)\bend\s*;" % kind, text, re.S)
+        if m:
+            for entry in m.group(1).split(";"):
+                if ":" in entry:
+                    k, v = entry.split(":", 1)
+                    try:
+                        val = _eval(v, env)
+                    except (NameError, ProgramSyntaxError):
+                        if kind != "options":
+                            raise
+                        val = v.strip().strip('"')  # option values may be bare names (_name_: my_program)
+                    if kind == "options":
+                        prog.options[k.strip()] = val
+                    else:
+                        env[k.strip()] = val
+            text = text[:m.start()] + text[m.end():]
+    if "_name_" in prog.options:
+        prog.name = prog.options.pop("_name_")
+    for stmt in text.split(";"):
+        s = " ".join(stmt.split())
+        if not s or s.split()[0] in ("use", "gate", "out", "func", "obs"):
+            continue
+        m = _OP_LINE.match(s)
+        if not m:
+            raise ProgramSyntaxError("cannot parse XIR statement %r" % s)
+        args, kwargs = _parse_args(m.group(2), env, ":") if m.group(2) and m.group(2).strip() else ([], {})
+        args = [np.array(a) if isinstance(a, list) else a for a in args]
+        prog.operations.append({"op": m.group(1), "args": args, "kwargs": kwargs, "modes": _parse_modes(m.group(3))})
+    return prog
+
+
+def _dumps_xir(prog):
+    out = []
+    opts = dict(prog.options)
+    if prog.name:
+        opts = {"_name_": prog.name, **opts}
+    if opts:
+        out.append("options:")
+        out.extend("    %s: %s;" % (k, _fmt(v)) for k, v in opts.items())
+        out.append("end;")
+        out.append("")
+    for op in prog.operations:
+        parts = [_fmt(a) for a in op.get("args", [])] + ["%s: %s" % (k, _fmt(v)) for k, v in op.get("kwargs", {}).items()]
+        out.append("%s%s | [%s];" % (op["op"], "(%s)" % ", ".join(parts) if parts else "", ", ".join(map(str, op["modes"]))))
+    return "\n".join(out) + ("\n" if out else "")
+
+
+# ------------------------------------------------------------------------------------ public API (io/__init__.py)
+def loads(s, ir="blackbird"):
+    """Load a circuit from a string (``sf.loads``, ``io/__init__.py:145-166``)."""
+    if ir == "blackbird":
+        return _loads_blackbird(s)
+    if ir == "xir":
+        return _loads_xir(s)
+    raise ValueError(f"'{ir}' not recognized as a valid IR option. Valid options are 'xir' and 'blackbird'.")
+
+
+def load(f, ir="blackbird"):
+    """Load a circuit from a ``.xbb`` / ``.xir`` file or file object (``sf.load``, ``io/__init__.py:169-237``)."""
+    if hasattr(f, "read"):
+        return loads(f.read(), ir)
+    name = os.fspath(f)
+    if ir not in ("blackbird", "xir"):
+        raise ValueError(f"'{ir}' not recognized as a valid IR option. Valid options are 'xir' and 'blackbird'.")
+    if ir == "blackbird" and name.endswith(".xir"):
+        ir = "xir"
+    with open(name) as fid:
+        return loads(fid.read(), ir)
+
+
+def dumps(prog, ir="blackbird"):
+    if ir == "blackbird":
+        return _dumps_blackbird(prog)
+    if ir == "xir":
+        return _dumps_xir(prog)
+    raise ValueError(f"'{ir}' not recognized as a valid IR option. Valid options are 'xir' and 'blackbird'.")
+
+
+def save(f, prog, ir="blackbird"):
+    """Write a circuit to a ``.xbb`` / ``.xir`` file (``sf.save``, ``io/__init__.py:67-142``: the extension is
+    appended when missing)."""
+    text = dumps(prog, ir)
+    if hasattr(f, "write"):
+        f.write(text)
+        return
+    name = os.fspath(f)
+    ext = ".xbb" if ir == "blackbird" else ".xir"
+    if not name.endswith(ext):
+        name += ext
+    with open(name, "w") as fid:
+        fid.write(text)
+
+
+# ------------------------------------------------------------------------------------ lowering
+def clements_rectangular(U, tol=1e-6):
+    """Rectangular (Clements et al. 2016) decomposition of an N x N unitary into the gate sequence the
+    reference front end emits for ``Interferometer(U)`` with its default mesh (``ops.py:2655-2718``,
+    ``decompositions.rectangular``): ``Rgate(phi), BSgate(theta, 0)`` pairs, one ``Rgate`` per mode, then
+    ``BSgate(-theta, 0), Rgate(-phi)`` pairs -- as backend calls on modes ``0 .. N-1``.  With
+    T(theta, phi) = BS(theta, 0) R_m(phi) on neighbouring modes (m, m+1), elements of U are nulled by
+    T^-1 from the right (even diagonals) and T from the left (odd diagonals) until a diagonal is left.
+    ``tol``: unitarity tolerance, the reference's default (``ops.py:2640``: stored scripts print 8 digits)."""
+    U = np.array(U, dtype=complex)
+    N = U.shape[0]
+    if U.shape != (N, N) or not np.allclose(U @ U.conj().T, np.eye(N), atol=tol):
+        raise ValueError("The input matrix is not unitary")
+    V = U.copy()
+    right, left = [], []
+    for i in range(N - 1):
+        for j in range(i + 1):
+            if i % 2 == 0:
+                r, m = N - 1 - j, i - j                     # null V[r, m] with columns (m, m+1)
+                a, b = V[r, m], V[r, m + 1]
+                phi = np.angle(a) - np.angle(b) if abs(a) > 0 and abs(b) > 0 else 0.0
+                theta = np.arctan2(abs(a), abs(b))
+                c, s, e = np.cos(theta), np.sin(theta), np.exp(-1j * phi)
+                Tinv = np.array([[e * c, e * s], [-s, c]])
+                V[:, [m, m + 1]] = V[:, [m, m + 1]] @ Tinv
+                right.append((m, theta, phi))
+            else:
+                m, col = N - 2 - i + j, j                   # null V[m+1, col] with rows (m, m+1)
+                a, b = V[m, col], V[m + 1, col]
+                phi = np.angle(-b) - np.angle(a) if abs(a) > 0 and abs(b) > 0 else 0.0
+                theta = np.arctan2(abs(b), abs(a))
+                c, s, e = np.cos(theta), np.sin(theta), np.exp(1j * phi)
+                T = np.array([[e * c, -s], [e * s, c]])
+                V[[m, m + 1], :] = T @ V[[m, m + 1], :]
+                left.append((m, theta, phi))
+    if np.abs(V - np.diag(np.diag(V))).max() > 10 * tol:
+        raise ValueError("rectangular decomposition did not converge")
+    calls = []
+    for m, theta, phi in right:
+        calls.append(("rotation", float(phi), m))
+        calls.append(("beamsplitter", float(theta), 0.0, m, m + 1))
+    for k in range(N):
+        calls.append(("rotation", float(np.angle(V[k, k])), k))
+    for m, theta, phi in reversed(left):
+        calls.append(("beamsplitter", float(-theta), 0.0, m, m + 1))
+        calls.append(("rotation", float(-phi), m))
+    return calls
+
+
+def _arg(args, kwargs, i, name, default=None):
+    if i < len(args):
+        return args[i]
+    if name in kwargs:
+        return kwargs[name]
+    if default is None:
+        raise TypeError("missing argument %r" % name)
+    return default
+
+
+def lower(op, args, kwargs, modes):
+    """One program operation -> ``BaseFock`` calls.  Gates whose first parameter is zero are skipped, as
+    ``Gate.apply`` does (``ops.py:494-509``)."""
+    a = lambda i, name, default=None: _arg(args, kwargs, i, name, default)  # noqa: E731
+    m = list(modes)
+    one = {"Dgate": ("displacement", ("r", "phi")), "Sgate": ("squeeze", ("r", "phi"))}
+    if op in one:
+        r, phi = a(0, "r"), a(1, "phi", 0.0)
+        return [] if r == 0 else [(one[op][0], float(r), float(phi), m[0])]
+    if op == "Rgate":
+        t = a(0, "theta")
+        return [] if t == 0 else [("rotation", float(t), m[0])]
+    if op == "Kgate":
+        k = a(0, "kappa")
+        return [] if k == 0 else [("kerr_interaction", float(k), m[0])]
+    if op == "Vgate":
+        g = a(0, "gamma")
+        return [] if g == 0 else [("cubic_phase", float(g), m[0])]
+    if op == "Fouriergate":
+        return [("rotation", math.pi / 2, m[0])]
+    if op == "Xgate":
+        x = a(0, "x")
+        return [] if x == 0 else [("displacement", abs(float(x)) / math.sqrt(2 * HBAR), 0.0 if x > 0 else math.pi, m[0])]
+    if op == "Zgate":
+        p = a(0, "p")
+        return [] if p == 0 else [("displacement", abs(float(p)) / math.sqrt(2 * HBAR),
+                                   math.pi / 2 if p > 0 else -math.pi / 2, m[0])]
+    if op == "Pgate":  # ops.py:1726-1732
+        s = float(a(0, "s"))
+        if s == 0:
+            return []
+        temp = s / 2
+        r = math.acosh(math.sqrt(1 + temp ** 2))
+        theta = math.atan(temp)
+        phi = -math.pi / 2 * np.sign(temp) - theta
+        return [("squeeze", r, float(phi), m[0]), ("rotation", theta, m[0])]
+    if op == "BSgate":
+        return [("beamsplitter", float(a(0, "theta", math.pi / 4)), float(a(1, "phi", 0.0)), m[0], m[1])] \
+            if a(0, "theta", math.pi / 4) != 0 else []
+    if op == "MZgate":
+        return [("mzgate", float(a(0, "phi_in")), float(a(1, "phi_ex")), m[0], m[1])]
+    if op == "S2gate":
+        r = a(0, "r")
+        return [] if r == 0 else [("two_mode_squeeze", float(r), float(a(1, "phi", 0.0)), m[0], m[1])]
+    if op == "CKgate":
+        k = a(0, "kappa")
+        return [] if k == 0 else [("cross_kerr_interaction", float(k), m[0], m[1])]
+    if op == "CXgate":  # ops.py:2149-2158
+        s = float(a(0, "s", 1.0))
+        if s == 0:
+            return []
+        r = math.asinh(-s / 2)
+        theta = 0.5 * math.atan2(-1.0 / math.cosh(r), -math.tanh(r))
+        return [("beamsplitter", theta, 0.0, m[0], m[1]), ("squeeze", r, 0.0, m[0]), ("squeeze", -r, 0.0, m[1]),
+                ("beamsplitter", theta + math.pi / 2, 0.0, m[0], m[1])]
+    if op == "CZgate":  # ops.py:2209-2216
+        s = float(a(0, "s", 1.0))
+        if s == 0:
+            return []
+        return [("rotation", -math.pi / 2, m[1])] + lower("CXgate", [s], {}, m) + [("rotation", math.pi / 2, m[1])]
+    if op == "Interferometer":
+        U = np.asarray(a(0, "U"), dtype=complex)
+        if U.shape != (len(m), len(m)):
+            raise ValueError("Interferometer matrix is %r for %d modes" % (U.shape, len(m)))
+        if kwargs.get("mesh", "rectangular") != "rectangular":
+            raise NotImplementedError("only the rectangular mesh is decomposed by the b200fock loader")
+        out = []
+        for c in clements_rectangular(U):
+            if c[1] == 0:
+                continue
+            out.append(c[:-1] + (m[c[-1]],) if c[0] == "rotation" else c[:-2] + (m[c[-2]], m[c[-1]]))
+        return out
+    if op == "LossChannel":
+        return [("loss", float(a(0, "T")), m[0])]
+    # ---- preparations
+    if op in ("Vacuum", "Vac"):
+        return [("prepare_vacuum_state", x) for x in m]
+    if op == "Fock":
+        return [("prepare_fock_state", int(a(0, "n", 0) if not (args or kwargs) else a(0, "n")), m[0])]
+    if op == "Coherent":
+        return [("prepare_coherent_state", float(a(0, "r", 0.0)), float(a(1, "phi", 0.0)), m[0])]
+    if op == "Squeezed":
+        return [("prepare_squeezed_state", float(a(0, "r", 0.0)), float(a(1, "p", 0.0)), m[0])]
+    if op == "DisplacedSqueezed":
+        return [("prepare_displaced_squeezed_state", float(a(0, "r_d", 0.0)), float(a(1, "phi_d", 0.0)),
+                 float(a(2, "r_s", 0.0)), float(a(3, "phi_s", 0.0)), m[0])]
+    if op == "Thermal":
+        return [("prepare_thermal_state", float(a(0, "n", 0.0)), m[0])]
+    if op == "Ket":
+        return [("prepare_ket_state", np.asarray(a(0, "state")), m)]
+    if op == "DensityMatrix":
+        return [("prepare_dm_state", np.asarray(a(0, "state")), m)]
+    # ---- measurements
+    if op == "MeasureFock":
+        sel = kwargs.get("select")
+        if sel is not None and not isinstance(sel, (list, tuple)):
+            sel = [sel]
+        return [("measure_fock", m, {"select": sel})] if sel is not None else [("measure_fock", m)]
+    if op in ("MeasureHomodyne", "MeasureX", "MeasureP", "MeasureHD"):
+        phi = {"MeasureX": 0.0, "MeasureP": math.pi / 2}.get(op)
+        if phi is None:
+            phi = float(a(0, "phi", 0.0))
+        sel = kwargs.get("select")
+        return [("measure_homodyne", phi, m[0], {"select": sel})]
+    raise NotImplementedError("operation %s is not supported by the Fock backend loader" % op)
+
+
+# ------------------------------------------------------------------------------------ state checkpoints
+CHECKPOINT_VERSION = 1
+
+
+def save_state(f, state):
+    """Write the ket / density matrix of a state object (``B200FockState``, or anything with ``data``,
+    ``is_pure``, ``num_modes``, ``cutoff_dim``) to an ``.npz`` checkpoint."""
+    data = np.asarray(state.data)
+    np.savez_compressed(f, data=data, pure=np.array(bool(state.is_pure)), num_modes=np.array(int(state.num_modes)),
+                        cutoff_dim=np.array(int(state.cutoff_dim)), version=np.array(CHECKPOINT_VERSION),
+                        layout=np.array("ket [D]*n | dm (ket_0, bra_0, ket_1, ...) [D]*2n, C order, complex128"))
+
+
+def load_state(f, backend=None):
+    """Read a checkpoint; with ``backend`` (already in a circuit of the same size) the state is prepared on
+    it (``prepare_ket_state`` / ``prepare_dm_state`` on all modes).  Returns ``(data, pure)``."""
+    with np.load(f, allow_pickle=False) as z:
+        if int(z["version"]) != CHECKPOINT_VERSION:
+            raise ValueError("unsupported checkpoint version %d" % int(z["version"]))
+        data, pure, n, D = z["data"], bool(z["pure"]), int(z["num_modes"]), int(z["cutoff_dim"])
+    if backend is not None:
+        if backend.get_cutoff_dim() != D or len(backend.get_modes()) != n:
+            raise ValueError("checkpoint holds %d modes at cutoff %d; the backend's circuit differs" % (n, D))
+        if getattr(data, "ndim", 0) in (n + 1, 2 * n + 1):
+            raise NotImplementedError("batched checkpoints are loaded entry by entry")
+        (backend.prepare_ket_state if pure else backend.prepare_dm_state)(data, list(range(n)))
+    return data, pure

@@ -83,6 +83,10 @@ class ShardedCircuit(DeviceCircuit):
             raise ValueError("exchange must be 'auto', 'p2p', 'push' or 'nccl'")
         self._p2p = False
         self._bufs = None
+        # gates that follow an exchange run part by part while the remaining parts are still in flight
+        # (peer-memory pull only): how many gates are executed that way, 0 = off
+        self._overlap_ops = int(opts.pop("exchange_overlap", 8))
+        self._xstream = None
         opts.pop("batch_size", None)
         opts["fuse"] = "fold"
         # lazy vacuum, sharded flavour: the part of a fresh program that fits one GPU runs REPLICATED on
@@ -350,12 +354,17 @@ class ShardedCircuit(DeviceCircuit):
         if replicated:
             self._build_from_replicated([all_ops[i] for i in replicated])
         self._fresh = False
-        for step in steps:
+        done_early = 0
+        for k, step in enumerate(steps):
             if step[0] == "run":
-                for i in step[1]:
+                for i in step[1][done_early:]:
                     self._exec(ops[i])
+                done_early = 0
             else:
-                self._exchange(sorted(self._pos[m] for m in step[1]))
+                # the first gates of the next run step can start on the parts of the new shard that have arrived
+                nxt = steps[k + 1][1] if k + 1 < len(steps) and steps[k + 1][0] == "run" else []
+                follow = [ops[i] for i in nxt[:self._overlap_ops]]
+                done_early = self._exchange(sorted(self._pos[m] for m in step[1]), follow)
 
     def _build_from_replicated(self, ops):
         """Lazy vacuum on a sharded state.  ``ops`` (a dependency-closed prefix of a fresh program that
@@ -527,18 +536,26 @@ class ShardedCircuit(DeviceCircuit):
             return
         L.call("b200_peer_barrier", C.byref(self._pflags), self._epoch, 60.0, self._stream())
 
-    def _exchange_p2p(self, T):
-        """Exchange without staging buffers and without host stalls: after a device-side barrier ONE launch
-        (``b200_exchange_copy``) moves this rank's whole share -- for every source rank a strided block of
+    def _exchange_p2p(self, T, follow=(), new_phys=None):
+        """Exchange without staging buffers and without host stalls: after a device-side barrier the launches
+        of ``b200_exchange_copy`` move this rank's whole share -- for every source rank a strided block of
         the old layout goes where it belongs in the new shard (the other ping-pong buffer), sources
         interleaved so that every NVLink peer is busy at once.  "p2p" pulls (the peers' old shards are the
-        sources), "push" posts stores into the peers' new shards."""
+        sources), "push" posts stores into the peers' new shards.
+
+        Overlap (pull only).  The new shard is cut along its outermost axis into its ``D / p_0`` index ranges
+        ("parts": contiguous, and independent of each other for every gate, because no gate acts on a sharded
+        axis).  Part c is pulled by its own launch on a side stream; as soon as it has landed, the gates of
+        ``follow`` run on it (launch views, ``DeviceCircuit._vptr``) while parts c+1.. are still crossing
+        NVLink: the link drives 48 CTAs, the other 100 SMs compute.  Returns ``len(follow)`` when it did."""
         g, n, D = self._g, self._axes(), self._trunc
         size = self._size()
         ls = [self._local_stride(p) for p in range(n)]
         sub = [D // p for p in self._ps]
         prof = self.__dict__.get("profile")
         push = self._xmode == "push"
+        cuda = self.device.type == "cuda"
+        parts = sub[0] if (follow and not push and sub[0] > 1) else 1
         if prof is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
@@ -546,60 +563,117 @@ class ShardedCircuit(DeviceCircuit):
         # the source of the previous exchange).  push: nobody still uses the buffer the peers will write.
         self._peer_barrier()
         dst = self._bufs[1 - self._cur]
-        axes = []  # (extent, source stride, destination stride), outermost first
-        for pos in range(n):
-            if pos < g:                       # new sharded remainder m_k <- source axis T[k]
-                axes.append((sub[pos], ls[T[pos]], ls[pos]))
-            elif pos in T:                    # new local axis T[k] <- source's remainder j_k on axis k
-                k = T.index(pos)
-                axes.append((sub[k], ls[k], ls[pos]))
-            else:
-                axes.append((D, ls[pos], ls[pos]))
-        merged = []
-        for a in axes:
-            if a[0] == 1:
-                continue
-            if merged and merged[-1][1] == a[1] * a[0] and merged[-1][2] == a[2] * a[0]:
-                merged[-1] = (merged[-1][0] * a[0], a[1], a[2])
-            else:
-                merged.append(a)
-        run = 1
-        if merged and merged[-1][1] == 1 and merged[-1][2] == 1:
-            run = merged.pop()[0]
-        if len(merged) > L.XCHG_MAX_AXES or self._world > L.XCHG_MAX_PEERS:
-            raise L.B200Error("exchange geometry exceeds the copy kernel's limits")
 
         def block(digits):
             return sum(digits[k] * sub[k] * ls[T[k]] for k in range(g))
 
-        d = L.XchgDesc()
-        d.n_axes, d.n_src, d.first_src, d.run = len(merged), self._world, self._rank, run
-        for j, (e, a, b) in enumerate(merged):
-            d.ext[j], d.ss[j], d.ds[j] = e, a, b
-        span_s = sum((e - 1) * a for e, a, _ in merged) + run - 1
-        span_d = sum((e - 1) * b for e, _, b in merged) + run - 1
-        for s in range(self._world):
-            sd = self._digits_of(s)
-            if push:   # my block for rank s goes straight into ITS new shard
-                d.src[s], d.dst[s] = self._buf.data_ptr(), self._peers[1 - self._cur][s].data_ptr()
-                d.src_base[s], d.dst_base[s] = block(sd), block(self._digits)
-            else:      # the receiver's digit selects the block, the sender's digit lands on axis T[k]
-                d.src[s], d.dst[s] = self._peers[self._cur][s].data_ptr(), dst.data_ptr()
-                d.src_base[s], d.dst_base[s] = block(self._digits), block(sd)
-            if d.src_base[s] + span_s >= size or d.dst_base[s] + span_d >= size:
-                raise L.B200Error("exchange block of rank %d leaves the shard" % s)
-        # this rank's own block stays in local HBM: plain copy by the CTAs the link does not need
-        L.call("b200_exchange_copy", C.byref(d), self._rank, int(self.__dict__.get("exchange_ctas", 0)),
-               self._stream())
-        if push:
-            self._peer_barrier()  # every peer's stores into my new shard have landed
+        def descriptor(part):
+            """block copy of the whole exchange (part None) or of one index of the new outermost axis"""
+            axes = []  # (extent, source stride, destination stride), outermost first
+            for pos in range(n):
+                if pos < g:                       # new sharded remainder m_k <- source axis T[k]
+                    axes.append((sub[pos], ls[T[pos]], ls[pos]))
+                elif pos in T:                    # new local axis T[k] <- source's remainder j_k on axis k
+                    k = T.index(pos)
+                    axes.append((sub[k], ls[k], ls[pos]))
+                else:
+                    axes.append((D, ls[pos], ls[pos]))
+            off_s = off_d = 0
+            if part is not None:
+                off_s, off_d = part * axes[0][1], part * axes[0][2]
+                axes[0] = (1, 0, 0)
+            merged = []
+            for a in axes:
+                if a[0] == 1:
+                    continue
+                if merged and merged[-1][1] == a[1] * a[0] and merged[-1][2] == a[2] * a[0]:
+                    merged[-1] = (merged[-1][0] * a[0], a[1], a[2])
+                else:
+                    merged.append(a)
+            run = 1
+            if merged and merged[-1][1] == 1 and merged[-1][2] == 1:
+                run = merged.pop()[0]
+            if len(merged) > L.XCHG_MAX_AXES or self._world > L.XCHG_MAX_PEERS:
+                raise L.B200Error("exchange geometry exceeds the copy kernel's limits")
+            d = L.XchgDesc()
+            d.n_axes, d.n_src, d.first_src, d.run = len(merged), self._world, self._rank, run
+            for j, (e, a, b) in enumerate(merged):
+                d.ext[j], d.ss[j], d.ds[j] = e, a, b
+            span_s = sum((e - 1) * a for e, a, _ in merged) + run - 1
+            span_d = sum((e - 1) * b for e, _, b in merged) + run - 1
+            for s in range(self._world):
+                sd = self._digits_of(s)
+                if push:   # my block for rank s goes straight into ITS new shard
+                    d.src[s], d.dst[s] = self._buf.data_ptr(), self._peers[1 - self._cur][s].data_ptr()
+                    d.src_base[s], d.dst_base[s] = block(sd) + off_s, block(self._digits) + off_d
+                else:      # the receiver's digit selects the block, the sender's digit lands on axis T[k]
+                    d.src[s], d.dst[s] = self._peers[self._cur][s].data_ptr(), dst.data_ptr()
+                    d.src_base[s], d.dst_base[s] = block(self._digits) + off_s, block(sd) + off_d
+                if d.src_base[s] + span_s >= size or d.dst_base[s] + span_d >= size:
+                    raise L.B200Error("exchange block of rank %d leaves the shard" % s)
+            return d
+
+        ctas = int(self.__dict__.get("exchange_ctas", 0))
+        if parts == 1:
+            # this rank's own block stays in local HBM: plain copy by the CTAs the link does not need
+            L.call("b200_exchange_copy", C.byref(descriptor(None)), self._rank, ctas, self._stream())
+            if push:
+                self._peer_barrier()  # every peer's stores into my new shard have landed
+            done = 0
+        else:
+            main = torch.cuda.current_stream(self.device) if cuda else None
+            if cuda:
+                if self._xstream is None:
+                    self._xstream = torch.cuda.Stream(self.device)
+                ready = torch.cuda.Event()
+                ready.record(main)              # behind the barrier: the peers' shards are final
+                self._xstream.wait_event(ready)
+            arrived = []
+            for c in range(parts):
+                d = descriptor(c)
+                if cuda:
+                    with torch.cuda.stream(self._xstream):
+                        if prof is not None and c == 0:
+                            x0 = torch.cuda.Event(enable_timing=True)
+                            x0.record(self._xstream)
+                        L.call("b200_exchange_copy", C.byref(d), self._rank, ctas, self._stream())
+                        ev = torch.cuda.Event(enable_timing=prof is not None and c == parts - 1)
+                        ev.record(self._xstream)
+                    arrived.append(ev)
+                else:
+                    L.call("b200_exchange_copy", C.byref(d), self._rank, ctas, self._stream())
+            if prof is not None and cuda:
+                # the transfer alone (first part issued .. last part landed), measured on the side stream while
+                # the main stream computes
+                prof.append(("exchange", 16 * size * (self._world - 1) // self._world, x0, arrived[-1]))
+            # the gates of `follow` on part c of the NEW shard, in the NEW layout
+            old_layout, old_cur, old_buf = list(self._phys), self._cur, self._buf
+            self._cur ^= 1
+            self._buf = dst
+            self._set_layout(new_phys)
+            part_elems = size // parts
+            try:
+                for c in range(parts):
+                    if cuda:
+                        main.wait_event(arrived[c])
+                    self._view = (c * part_elems, part_elems)
+                    for op in follow:
+                        self._exec(op)
+            finally:
+                self._view = None
+                self._set_layout(old_layout)   # _exchange() installs the new layout and buffer for good
+                self._cur, self._buf = old_cur, old_buf
+            done = len(follow)
         if prof is not None:
             ev1.record()
             nbytes = 16 * size * (self._world - 1) // self._world
-            prof.append(("exchange/p2p_push" if push else "exchange/p2p_pull", nbytes, ev0, ev1))
-            prof.append(("exchange", nbytes, ev0, ev1))
+            tag = "exchange/p2p_push" if push else ("exchange/p2p_pull" if parts == 1 else "exchange/p2p_pull+gates")
+            prof.append((tag, nbytes, ev0, ev1))
+            if parts == 1:
+                prof.append(("exchange", nbytes, ev0, ev1))
         self._cur ^= 1
         self._buf = dst
+        return done
 
     # ------------------------------------------------------------------ the exchange
     def _contig(self, exts):
@@ -609,22 +683,26 @@ class ShardedCircuit(DeviceCircuit):
             acc *= e
         return list(reversed(st))
 
-    def _exchange(self, T):
-        """Swap sharded axis k with local axis T[k] for every k."""
+    def _exchange(self, T, follow=()):
+        """Swap sharded axis k with local axis T[k] for every k.  ``follow``: the gates that come next; the
+        peer-memory pull exchange may run them part by part as the parts of the new shard arrive.  Returns
+        how many of them it has executed."""
         g, n = self._g, self._axes()
         assert len(T) == g and all(t >= g for t in T)
         self._own()  # the unpack writes in place: never into a buffer a state object still shares
-        if self._p2p:
-            self._exchange_p2p(T)
-        else:
-            self._exchange_nccl(T)
         phys = list(self._phys)
         for k in range(g):
             phys[k], phys[T[k]] = phys[T[k]], phys[k]
+        done = 0
+        if self._p2p:
+            done = self._exchange_p2p(T, follow, phys)
+        else:
+            self._exchange_nccl(T)
         self._set_layout(phys)
         self._fresh = False
         self.exchanges += 1
         self.exchange_bytes += 16 * self._size() * (self._world - 1) // self._world
+        return done
 
     def _exchange_nccl(self, T):
         """pack (strided gather) -> all_to_all_single -> unpack (strided gather)."""
@@ -908,6 +986,47 @@ class ShardedCircuit(DeviceCircuit):
     def _apply_dense_now(self, U, mode):
         self._emit_dense(U, mode)
         self._run_queue()
+
+    # ------------------------------------------------------------------ per-rank checkpoints
+    def save_shard(self, directory):
+        """Write this rank's shard and the layout it is stored in to ``directory`` (one ``.npy`` + one
+        ``.json`` per rank): the checkpoint of a state that does not fit one host.  Collective."""
+        import json
+        import os
+
+        self._flush()
+        os.makedirs(directory, exist_ok=True)
+        self._sync()
+        np.save(os.path.join(directory, "shard_%04d.npy" % self._rank), self._buf.cpu().numpy())
+        with open(os.path.join(directory, "shard_%04d.json" % self._rank), "w") as f:
+            json.dump({"version": 1, "world": self._world, "rank": self._rank, "num_modes": self._num_modes,
+                       "cutoff_dim": self._trunc, "pure": bool(self._pure), "factors": self._ps,
+                       "phys": [int(x) for x in self._phys], "elements": int(self._size())}, f)
+        dist.barrier(group=self._pg)
+
+    def load_shard(self, directory):
+        """Restore a state written by ``save_shard`` with the same world size, cutoff and mode count."""
+        import json
+        import os
+
+        with open(os.path.join(directory, "shard_%04d.json" % self._rank)) as f:
+            meta = json.load(f)
+        if (meta["world"], meta["num_modes"], meta["cutoff_dim"], meta["factors"]) != \
+                (self._world, self._num_modes, self._trunc, self._ps):
+            raise ValueError("checkpoint was written by %d ranks for %d modes at cutoff %d; this circuit differs"
+                             % (meta["world"], meta["num_modes"], meta["cutoff_dim"]))
+        self._flush()
+        if bool(meta["pure"]) != self._pure:
+            self._pure = bool(meta["pure"])
+            self._bufs = None
+        self._set_layout(meta["phys"])
+        self._alloc()
+        data = np.load(os.path.join(directory, "shard_%04d.npy" % self._rank))
+        if data.size != self._size():
+            raise ValueError("shard of rank %d has %d elements, expected %d" % (self._rank, data.size, self._size()))
+        self._buf.copy_(torch.from_numpy(data).to(self.device))
+        self._pending, self._opq, self._untouched, self._fresh = {}, [], set(), False
+        dist.barrier(group=self._pg)
 
     # ------------------------------------------------------------------ not sharded yet
     def _unsupported(self, *a, **k):

@@ -40,7 +40,7 @@ def main():
     B.b200_arm(argparse.Namespace(gpus=world, steps=2, warmup=1, impl="b200", modes=int(sys.argv[1]),
                                   cutoff=int(sys.argv[2]), no_cpu_baseline=True, workload="c2", batch=2,
                                   exchange=sys.argv[3], fuse="fold", no_parity=False, no_ten_mode=False,
-                                  parity_probs=12,
+                                  parity_probs=12, exchange_overlap=8,
                                   from_vacuum=len(sys.argv) > 4 and sys.argv[4] == "from_vacuum"))
 
 

@@ -85,6 +85,26 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
         sys.exit(0 if ok else 1)
+    if "ckpt" in flags:
+        # per-rank checkpoint: save the shards, wipe the circuit, load them back -- same state
+        import tempfile
+
+        from strawberryfields_b200 import sharding
+
+        want = st.data.copy()
+        path = [tempfile.mkdtemp() if dist.get_rank() == 0 else None]
+        dist.broadcast_object_list(path, src=0)
+        be.circuit.save_shard(path[0])
+        be.reset()
+        be.circuit.load_shard(path[0])
+        got = be.state().data
+        ok = bool(np.abs(got - want).max() == 0 and abs(be.state().trace() - st.trace()) < 1e-15)
+        be.rotation(0.3, 0)   # the restored circuit keeps working
+        ok = ok and abs(be.state().trace() - st.trace()) < 1e-12
+        print(json.dumps({"rank": dist.get_rank(), "world": dist.get_world_size(), "ok": ok}))
+        dist.barrier()
+        dist.destroy_process_group()
+        sys.exit(0 if ok else 1)
     from strawberryfields_b200 import sharding
 
     first_layout = list(next(iter(sharding._PLANS.values()))[0])  # layout the planner chose for |0..0>

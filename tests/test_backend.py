@@ -258,3 +258,79 @@ def test_wrong_strides_fail_on_the_host(monkeypatch):
     c._buf = c._buf[: n // 2]
     with pytest.raises(lib.B200Error, match="state buffer"):
         c._k_gate1(U, 1, 0)                                                       # buffer smaller than the state
+
+
+# ---------------------------------------------------------------------------- batched preparation / measurement
+# TF-backend batch semantics (tfbackend/circuit.py:343 prepare_multimode, :612 measure_fock)
+@pytest.mark.parametrize("lazy", [False, True])
+def test_batched_preparations_and_measure_fock(host_backend, lazy):
+    from oracle.fock_oracle import OracleBackend
+
+    D, B, n = 5, 4, 3
+    rs = np.random.RandomState(8)
+    r = rs.uniform(0.1, 0.5, B)
+    th = rs.uniform(0, 1.2, B)
+    be = host_backend(lazy_vacuum=lazy)
+    be.begin_circuit(n, cutoff_dim=D, batch_size=B)
+
+    def program(b_, rr, tt):
+        b_.prepare_coherent_state(rr, 0.3, 0)         # per-entry parameters
+        b_.prepare_fock_state(1, 1)                   # the same ket for every entry
+        b_.prepare_squeezed_state(0.2, 0.1, 2)
+        b_.beamsplitter(tt, 0.2, 0, 1)
+        b_.beamsplitter(0.4, 0.0, 1, 2)
+        b_.kerr_interaction(0.1, 0)
+
+    program(be, r, th)
+    kets = be.state().ket()
+    obs = []
+    for b in range(B):
+        ob = OracleBackend()
+        ob.begin_circuit(n, cutoff_dim=D)
+        # the oracle (like the reference) would mix the state on single-mode preparations: prepare the product ket
+        from strawberryfields_b200.circuit import _coherent, _squeezed
+
+        f1 = np.zeros(D, dtype=complex)
+        f1[1] = 1
+        ob.prepare_ket_state(np.multiply.outer(np.multiply.outer(_coherent(r[b], 0.3, D), f1), _squeezed(0.2, 0.1, D)),
+                             [0, 1, 2])
+        ob.beamsplitter(th[b], 0.2, 0, 1)
+        ob.beamsplitter(0.4, 0.0, 1, 2)
+        ob.kerr_interaction(0.1, 0)
+        assert np.abs(kets[b] - ob.state().data).max() < TOL
+        obs.append(ob)
+    # seeded measurement: one uniform per entry, in batch order -- the same draws as B sequential oracle runs
+    np.random.seed(3)
+    got = be.measure_fock([2, 0])
+    assert got.shape == (B, 2)
+    np.random.seed(3)
+    post = be.state().ket()
+    for b in range(B):
+        want = obs[b].measure_fock([2, 0])
+        assert np.array_equal(got[b], np.asarray(want).reshape(-1))
+        assert np.abs(post[b] - obs[b].state().data).max() < TOL
+    # post-selection: one list for all entries, or one per entry
+    be.reset()
+    program(be, r, th)
+    sel = np.array([[0, 1], [1, 0], [0, 0], [1, 1]])
+    out = be.measure_fock([0, 2], select=sel)
+    assert np.array_equal(out, sel)
+    post = be.state().ket()
+    for b in range(B):
+        ob = OracleBackend()
+        ob.begin_circuit(n, cutoff_dim=D)
+        f1 = np.zeros(D, dtype=complex)
+        f1[1] = 1
+        ob.prepare_ket_state(np.multiply.outer(np.multiply.outer(_coherent(r[b], 0.3, D), f1), _squeezed(0.2, 0.1, D)),
+                             [0, 1, 2])
+        ob.beamsplitter(th[b], 0.2, 0, 1)
+        ob.beamsplitter(0.4, 0.0, 1, 2)
+        ob.kerr_interaction(0.1, 0)
+        ob.measure_fock([0, 2], select=[int(x) for x in sel[b]])
+        assert np.abs(post[b] - ob.state().data).max() < TOL
+    with pytest.raises(ValueError, match="shape of 'select'"):
+        be.measure_fock([0, 2], select=[1, 0, 0])
+    with pytest.raises(NotImplementedError):
+        be.prepare_fock_state(1, 0)                   # mode 0 is no longer the untouched vacuum
+    with pytest.raises(NotImplementedError):
+        be.prepare_ket_state(np.ones((D, D)) / D, [1, 2])

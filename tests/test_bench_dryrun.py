@@ -42,7 +42,7 @@ def bench(monkeypatch):
 def _args(**kw):
     base = dict(gpus=1, steps=2, warmup=1, impl="b200", modes=4, cutoff=3, no_cpu_baseline=True, workload="c2",
                 batch=2, exchange="auto", fuse="fold", from_vacuum=False, no_parity=False, no_ten_mode=False,
-                parity_probs=12)
+                parity_probs=12, exchange_overlap=8)
     base.update(kw)
     return argparse.Namespace(**base)
 

@@ -1,0 +1,276 @@
+"""Program I/O: Blackbird / XIR loaders and writers and the state checkpoint
+(``strawberryfields_b200/io.py``; reference: ``strawberryfields/io/__init__.py:67,145,169``).
+The loaders are checked on the reference's own example script, on round trips, against the oracle,
+and -- where /root/reference exists -- against the reference front end compiling the same program."""
+import io as _io
+import os
+
+import numpy as np
+import pytest
+
+from fake_lib import FakeLib
+from strawberryfields_b200 import io as bio
+from strawberryfields_b200 import workloads as W
+
+X8 = """\
+name example_job_X8
+version 1.0
+target X8_01 (shots = 20)
+
+complex array U[4, 4] =
+    -0.13879438-0.47517904j, -0.29303954-0.47264099j, -0.43951987+0.12977568j, -0.03496718-0.48418713j
+    0.06065372-0.11292765j, 0.54733962+0.1215551j, -0.50721513+0.56195975j, -0.15923161+0.26606674j
+    0.42212573-0.53182417j, -0.2642572+0.50625182j, 0.19448705+0.28321781j, 0.30281396-0.05582391j
+    0.43097587-0.30288974j, 0.07419772-0.21155126j, 0.28335618-0.13633175j, -0.75113453+0.09580304j
+
+# Initial states are two-mode squeezed states
+S2gate(1.0, 0.0) | [0, 4]
+S2gate(1.0, 0.0) | [1, 5]
+S2gate(1.0, 0.0) | [3, 7]
+
+Interferometer(U) | [0, 1, 2, 3]
+BSgate(0.543, 0.123) | [2, 0]
+Rgate(0.453) | 1
+MZgate(0.65, -0.54) | [2, 3]
+
+Interferometer(U) | [4, 5, 6, 7]
+BSgate(0.543, 0.123) | [6, 4]
+Rgate(0.453) | 5
+MZgate(0.65, -0.54) | [6, 7]
+
+MeasureFock() | [0, 1, 2, 3, 4, 5, 6, 7]
+"""
+
+
+@pytest.fixture
+def host(monkeypatch):
+    from strawberryfields_b200 import circuit, lib
+
+    monkeypatch.setattr(lib, "_lib", FakeLib())
+    monkeypatch.setattr(circuit, "_TEST_HOST_MODE", True)
+
+
+def test_blackbird_header_arrays_and_operations():
+    prog = bio.loads(X8)
+    assert prog.name == "example_job_X8" and prog.version == "1.0"
+    assert prog.target == {"name": "X8_01", "options": {"shots": 20}} and prog.run_options == {"shots": 20}
+    assert prog.num_subsystems == 8 and len(prog.operations) == 12
+    op = prog.operations[3]
+    assert op["op"] == "Interferometer" and op["modes"] == [0, 1, 2, 3] and op["args"][0].shape == (4, 4)
+    assert op["args"][0][1, 2] == -0.50721513 + 0.56195975j
+    assert prog.operations[5] == {"op": "Rgate", "args": [0.453], "kwargs": {}, "modes": [1]}
+    assert prog.operations[-1]["op"] == "MeasureFock" and prog.operations[-1]["args"] == []
+
+
+def test_reference_example_file_loads_if_present():
+    path = "/root/reference/examples/example_job_X8.xbb"
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present")
+    prog = bio.load(path)
+    assert [o["op"] for o in prog.operations] == [o["op"] for o in bio.loads(X8).operations]
+
+
+def test_expressions_variables_and_keywords():
+    prog = bio.loads("""name t
+version 1.0
+float alpha = 0.3423
+int n = 2
+Coherent(alpha, sqrt(pi)) | 0
+Sgate(-alpha*2, phi=pi/4) | 1
+Fock(n) | 2
+MeasureHomodyne(phi=0.43, select=0.32) | 2   # trailing comment
+MeasureX | 0
+""")
+    ops = prog.operations
+    assert ops[0]["args"] == [0.3423, np.sqrt(np.pi)]
+    assert ops[1]["args"] == [-0.6846] and ops[1]["kwargs"] == {"phi": np.pi / 4}
+    assert ops[2]["args"] == [2]
+    assert ops[3]["kwargs"] == {"phi": 0.43, "select": 0.32} and ops[4] == {"op": "MeasureX", "args": [], "kwargs": {}, "modes": [0]}
+    calls = prog.calls()
+    assert calls[0] == ("prepare_coherent_state", 0.3423, float(np.sqrt(np.pi)), 0)
+    assert calls[-2] == ("measure_homodyne", 0.43, 2, {"select": 0.32}) and calls[-1] == ("measure_homodyne", 0.0, 0, {"select": None})
+
+
+@pytest.mark.parametrize("bad,exc", [("Sgate(0.3 | 0", bio.ProgramSyntaxError), ("Sgate(foo) | 0", NameError),
+                                     ("for int m in 0:3\n    Sgate(0.1) | m", NotImplementedError),
+                                     ("Dgate(q0) | 1", NotImplementedError), ("Sgate({r}) | 0", NotImplementedError),
+                                     ("Sgate(__import__('os')) | 0", bio.ProgramSyntaxError)])
+def test_bad_scripts_are_refused(bad, exc):
+    with pytest.raises(exc):
+        bio.loads("name x\nversion 1.0\n" + bad + "\n")
+
+
+def test_invalid_ir_names():
+    with pytest.raises(ValueError, match="not recognized as a valid IR option"):
+        bio.loads("", ir="qasm")
+    with pytest.raises(ValueError, match="not recognized as a valid IR option"):
+        bio.dumps(bio.CircuitProgram(), ir="qasm")
+
+
+def test_xir_script():
+    prog = bio.loads("""options:
+    _name_: test_program;
+    cutoff_dim: 5;
+    shots: 2;
+end;
+use xstd;
+Vacuum | [1];
+Squeezed(0.12, 0.0) | [2];
+Sgate(1, 0.0) | [0];      // a comment
+S2gate(0.543, -0.12) | [0, 3];
+Interferometer([[(0.6+0j), (0.8+0j)], [(-0.8+0j), (0.6+0j)]]) | [0, 1];
+MeasureHomodyne(phi: 0.43, select: 0.32) | [2];
+""", ir="xir")
+    assert prog.name == "test_program" and prog.backend_options == {"cutoff_dim": 5} and prog.run_options == {"shots": 2}
+    assert [o["op"] for o in prog.operations] == ["Vacuum", "Squeezed", "Sgate", "S2gate", "Interferometer", "MeasureHomodyne"]
+    assert prog.operations[3] == {"op": "S2gate", "args": [0.543, -0.12], "kwargs": {}, "modes": [0, 3]}
+    assert prog.operations[4]["args"][0].shape == (2, 2) and prog.operations[5]["kwargs"] == {"phi": 0.43, "select": 0.32}
+
+
+@pytest.mark.parametrize("ir", ["blackbird", "xir"])
+def test_save_load_round_trip(ir, tmp_path):
+    prog = bio.loads(X8)
+    path = tmp_path / "prog"
+    bio.save(str(path), prog, ir=ir)
+    written = str(path) + (".xbb" if ir == "blackbird" else ".xir")
+    assert os.path.exists(written)            # the extension is appended (io/__init__.py:118-121)
+    back = bio.load(written, ir=ir)
+    assert back.name == prog.name and len(back.operations) == len(prog.operations)
+    for a, b in zip(prog.operations, back.operations):
+        assert a["op"] == b["op"] and a["modes"] == b["modes"] and a["kwargs"] == b["kwargs"]
+        for x, y in zip(a["args"], b["args"]):
+            assert np.allclose(x, y, atol=0, rtol=0)
+    buf = _io.StringIO()
+    bio.save(buf, prog, ir=ir)
+    assert bio.loads(buf.getvalue(), ir=ir).num_subsystems == 8
+
+
+@pytest.mark.parametrize("N", [2, 3, 4, 5, 8])
+def test_clements_mesh_reproduces_the_unitary(N):
+    rng = np.random.RandomState(N)
+    A = rng.randn(N, N) + 1j * rng.randn(N, N)
+    U, _ = np.linalg.qr(A)
+    calls = bio.clements_rectangular(U)
+    assert np.abs(W.interferometer_unitary(N, calls) - U).max() < 1e-13
+    assert sum(c[0] == "beamsplitter" for c in calls) == N * (N - 1) // 2
+    assert all(abs(c[-1] - c[-2]) == 1 for c in calls if c[0] == "beamsplitter")   # neighbouring modes only
+    # the structure the reference emits: (R, BS) pairs, one R per mode, (BS, R) pairs
+    kinds = [c[0][0] for c in calls]
+    first = N * (N - 1) // 2 - sum(1 for i in range(1, N - 1, 2) for _ in range(i + 1))
+    assert kinds == ["r", "b"] * first + ["r"] * N + ["b", "r"] * (N * (N - 1) // 2 - first)
+    with pytest.raises(ValueError, match="not unitary"):
+        bio.clements_rectangular(A)
+
+
+def test_reference_compiled_mesh_instances_agree(golden_dir):
+    """tests/golden/interferometer_n*.json hold gate lists the reference front end compiled for given
+    unitaries: our mesh realises the same unitary with the same gate structure."""
+    import json
+
+    for N in (4, 5):
+        path = os.path.join(golden_dir, "interferometer_n%d.json" % N)
+        ref = json.load(open(path))
+        if "U_re" not in ref:
+            pytest.skip("fixture holds no unitary")
+        U = np.array(ref["U_re"]) + 1j * np.array(ref["U_im"])
+        calls = bio.clements_rectangular(U)
+        assert np.abs(W.interferometer_unitary(N, calls) - U).max() < 1e-12
+
+
+def test_program_runs_and_matches_the_oracle(host):
+    """a loaded script on the plugin == the same calls on the oracle (decompositions included)"""
+    from oracle.fock_oracle import OracleBackend
+    from strawberryfields_b200.backend import B200FockBackend
+
+    rng = np.random.RandomState(4)
+    U, _ = np.linalg.qr(rng.randn(3, 3) + 1j * rng.randn(3, 3))
+    rows = "\n".join("    " + ", ".join("%r%s%rj" % (float(z.real), "+" if z.imag >= 0 else "-", abs(float(z.imag))) for z in row) for row in U)
+    script = """name mixed_bag
+version 1.0
+complex array U[3, 3] =
+%s
+Squeezed(0.3, 0.2) | 0
+Coherent(0.4, 1.0) | 1
+Interferometer(U) | [2, 0, 1]
+Xgate(0.3) | 0
+Zgate(-0.2) | 1
+Pgate(0.4) | 2
+CXgate(0.3) | [0, 1]
+CZgate(-0.2) | [1, 2]
+Fouriergate() | 0
+Kgate(0.1) | 1
+CKgate(0.2) | [0, 2]
+Vgate(0.05) | 2
+LossChannel(0.9) | 1
+""" % rows
+    prog = bio.loads(script)
+    be = B200FockBackend()
+    prog.run(be, cutoff_dim=5)
+    ob = OracleBackend()
+    ob.begin_circuit(3, cutoff_dim=5)
+    for c in prog.calls():
+        getattr(ob, c[0])(*c[1:])
+    assert np.abs(be.state().dm() - ob.state().dm()).max() < 1e-12
+
+
+def test_measurement_samples_are_returned(host):
+    from strawberryfields_b200.backend import B200FockBackend
+
+    prog = bio.loads("name m\nversion 1.0\nFock(2) | 0\nFock(1) | 1\nBSgate(0.0, 0.0) | [0, 1]\nMeasureFock() | [1, 0]\n")
+    samples = prog.run(B200FockBackend(), cutoff_dim=4)
+    assert samples == {1: [1], 0: [2]}
+    with pytest.raises(ValueError, match="cutoff_dim"):
+        prog.run(B200FockBackend())
+
+
+@pytest.mark.parametrize("pure", [True, False])
+def test_state_checkpoint_round_trip(host, pure, tmp_path):
+    from strawberryfields_b200.backend import B200FockBackend
+
+    be = B200FockBackend()
+    be.begin_circuit(3, cutoff_dim=4, pure=pure)
+    W.run_calls(be, W.config2_circuit(3, seed=2))
+    st = be.state()
+    path = str(tmp_path / "ckpt.npz")
+    bio.save_state(path, st)
+    b2 = B200FockBackend()
+    b2.begin_circuit(3, cutoff_dim=4)
+    data, was_pure = bio.load_state(path, b2)
+    assert was_pure == pure and np.array_equal(data, st.data)
+    assert b2.state().is_pure == pure and np.abs(b2.state().data - st.data).max() < 1e-15
+    b3 = B200FockBackend()
+    b3.begin_circuit(2, cutoff_dim=4)
+    with pytest.raises(ValueError, match="checkpoint holds"):
+        bio.load_state(path, b3)
+
+
+@pytest.mark.reference
+def test_lowering_equals_the_reference_front_end():
+    """Differential: the reference front end (blackbird stubbed away, so the program is built with its own
+    ops) compiles the same operations with its ``fock`` compiler; the backend call lists must produce the same
+    state on the oracle."""
+    from oracle import ref_shim
+    from oracle.fock_oracle import OracleBackend
+
+    sf = ref_shim.install()
+    from strawberryfields import ops
+
+    prog = bio.loads(X8.replace("S2gate(1.0", "S2gate(0.3").replace("| [0, 4]", "| [0, 2]").replace("| [1, 5]", "| [1, 3]")
+                     .replace("S2gate(0.3, 0.0) | [3, 7]\n", "").split("Interferometer(U) | [4, 5, 6, 7]")[0])
+    # (q[2], q[0]) would hit the reference's pure-state axis bug: keep the pair ascending
+    assert prog.operations[3]["modes"] == [2, 0]
+    prog.operations[3]["modes"] = [0, 2]
+    # the script prints U to 8 digits; both sides get the same exactly unitary matrix
+    prog.operations[2]["args"][0] = np.linalg.qr(prog.operations[2]["args"][0])[0]
+    sfp = sf.Program(4)
+    with sfp.context as q:
+        for op in prog.operations:
+            getattr(ops, op["op"])(*op["args"], **op["kwargs"]) | [q[i] for i in op["modes"]]
+    eng = sf.Engine("fock", backend_options={"cutoff_dim": 5})
+    want = eng.run(sfp).state
+    ob = OracleBackend()
+    ob.begin_circuit(4, cutoff_dim=5)
+    for c in prog.calls():
+        getattr(ob, c[0])(*c[1:])
+    got = ob.state()
+    assert np.abs(got.data - want.data).max() < 1e-12

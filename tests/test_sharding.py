@@ -101,6 +101,11 @@ def test_sharded_density_matrices_match_oracle_gloo(world, n, D, exchange, flag)
     _run("host", world, n, D, exchange, flags=[flag])
 
 
+def test_sharded_checkpoint_round_trip_gloo():
+    """ShardedCircuit.save_shard / load_shard (on-disk checkpoint of a sharded ket)"""
+    _run("host", 4, 5, 6, "p2p", flags=["ckpt"])
+
+
 @pytest.mark.parametrize("exchange", ["auto", "p2p"])
 def test_state_object_survives_reset_gloo(exchange):
     """eng.run() -> eng.reset() -> result.state: the snapshot keeps its buffer in every exchange mode, and
