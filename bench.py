@@ -477,7 +477,8 @@ def b200_arm(args):
         calls = W.config3_circuit(n_modes, seed=42)
         elements = D ** (2 * n_modes)
         shard_kw = {"pure": False}
-        wl_name = "3: %d-mode mixed state (density matrix), Sgate/BSgate layers + LossChannel(0.9) per mode" % n_modes
+        wl_name = ("3: %d-mode mixed state (density matrix), Sgate/BSgate layers + LossChannel(0.9) per mode, "
+                   "then MeasureFock on all modes" % n_modes)
     elif args.workload == "c4":    # BASELINE config 4: QNN layer, 6 modes, batch of 64 pure states
         n_modes = args.modes or 6
         calls = W.config4_circuit(n_modes, batch=args.batch, seed=42)
@@ -506,10 +507,17 @@ def b200_arm(args):
     # i.e. the steady-state cost of the kernels alone.
     value_kw = dict(shard_kw, lazy_vacuum=bool(args.from_vacuum))
 
+    measured = {}
+
     def one_step(b):
-        if args.from_vacuum:
+        # config 3 ends with MeasureFock on every mode (BASELINE config 3): the measurement is part of the step,
+        # and because it collapses the state every step starts from a fresh density matrix
+        if args.from_vacuum or args.workload == "c3":
             b.reset(pure=args.workload != "c3")
         W.run_calls(b, calls)
+        if args.workload == "c3":
+            np.random.seed(7)
+            measured["outcome"] = np.asarray(b.measure_fock(list(range(n_modes)))).reshape(-1).tolist()
         b.circuit._flush()
 
     be = B200FockBackend()
@@ -669,8 +677,10 @@ def b200_arm(args):
                       % (local_elements * 16 / 1e9),
                 "passes_per_step": sum(v[2] for v in by_tag.values()),
                 "gate_queue": args.fuse,
-                "state_at_step_start": ("vacuum (reset inside the timed step, lazy-vacuum factors)"
-                                        if args.from_vacuum else "dense state left by the previous step"),
+                "state_at_step_start": ("vacuum (reset inside the timed step, lazy-vacuum factors)" if args.from_vacuum
+                                        else "vacuum density matrix (reset inside the timed step; the step ends with "
+                                             "MeasureFock on all modes, seed 7)" if args.workload == "c3"
+                                        else "dense state left by the previous step"),
             },
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
             "hbm_GBps_per_gpu_whole_step": sum(v[0] for v in by_tag.values()) * args.steps
@@ -697,6 +707,8 @@ def b200_arm(args):
                 if sel:
                     line["exchange"][part] = {"ms": sum(t for _, t in sel) / len(sel) * 1e3,
                                               "GBps": sum(nb for nb, _ in sel) / sum(t for _, t in sel) / 1e9}
+        if measured:
+            line["measure_fock_outcome"] = measured["outcome"]   # tests/golden/ref_config3_full.npz holds the oracle's
         if parity is not None:
             line["parity"] = parity
             line["single_gpu_same_workload_ms"] = single_ms
@@ -728,7 +740,7 @@ def main():
     ap.add_argument("--fuse", default="fold", choices=["tile", "fold", "off"],
                     help="gate queue: diagonal / same-mode folding (default), + multi-gate tile passes, "
                          "or one pass per gate")
-    ap.add_argument("--exchange-overlap", type=int, default=8,
+    ap.add_argument("--exchange-overlap", type=int, default=4,
                     help="sharded arm: gates behind an exchange that run part by part while the rest of the shard is "
                          "still crossing NVLink (0 = off)")
     ap.add_argument("--no-parity", action="store_true", help="sharded arm: skip the parity block")

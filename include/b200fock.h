@@ -212,7 +212,7 @@ int b200_scale(b200_c128* dev, int64_t n, double re, double im, const double* di
  * `first_src`.  local_src >= 0 (then == first_src): that source and its destination are both
  * local; its block is copied with plain loads / stores by the CTAs the link does not need
  * (-1: every source goes through the bulk path).  bulk_ctas: CTAs driving the bulk path,
- * 0 = default (48 next to a local block, else one per SM).                                       */
+ * 0 = default (32 next to a local block, else one per SM).                                       */
 #define B200_XCHG_MAX_AXES 12
 #define B200_XCHG_MAX_PEERS 32
 typedef struct {

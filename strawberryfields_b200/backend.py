@@ -162,7 +162,7 @@ class B200FockBackend(_Base):
             group = None if shard is True else shard
             self.circuit = ShardedCircuit(num_subsystems, cutoff_dim, group=group, pure=pure,
                                           exchange=kwargs.get("exchange", "auto"),
-                                          exchange_overlap=kwargs.get("exchange_overlap", 8), **self._options)
+                                          exchange_overlap=kwargs.get("exchange_overlap", 4), **self._options)
         else:
             self.circuit = DeviceCircuit(num_subsystems, cutoff_dim, pure, batch_size=batch_size, **self._options)
         self._modemap = ModeMap(num_subsystems)

@@ -26,7 +26,9 @@ constexpr int XC_THREADS = 512;           // 16 warps: all of them copy in the C
 constexpr int XC_STAGES = 3;
 constexpr int XC_STAGE_BYTES = 16 * 1024;
 constexpr int XC_SMEM = XC_WARPS * XC_STAGES * XC_STAGE_BYTES;
-constexpr int XC_BULK_CTAS = 48;          // CTAs that drive NVLink (probe: 32 CTAs already reach 667-689 GB/s)
+constexpr int XC_BULK_CTAS = 32;          // CTAs that drive NVLink next to a local block (probe: 32 CTAs reach
+                                          // 667-689 GB/s, 64: 660-712, all 148: 676-712); the rest stay free for the
+                                          // gate kernels that overlap the exchange
 constexpr int XC_SEG = 256;               // elements of a run one warp copies at a time (8 per lane in flight)
 
 // offsets of run q (0 <= q < n_outer) of the block copy: mixed-radix decode over the outer axes
