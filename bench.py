@@ -57,17 +57,20 @@ def measured_peaks():
 
 
 def ncu_traffic(kernel, elements_per_launch):
-    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture
-    (profiles/r01_ncu_traffic.json, taken on config 2: 1e8 amplitudes per launch); None for any
-    other launch size -- never extrapolated."""
-    path = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
-    if not os.path.exists(path) or elements_per_launch != 10 ** 8:
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full captures
+    (profiles/r0*_ncu_traffic.json, taken on config 2: 1e8 amplitudes per launch; the streaming kernel's
+    capture is round 1's, the kernel is unchanged); None for any other launch size -- never extrapolated."""
+    if elements_per_launch != 10 ** 8:
         return None
-    with open(path) as f:
-        table = json.load(f)["bytes_per_launch"]
-    for name, val in table.items():
-        if kernel in name:
-            return val
+    for name in ("r02_ncu_traffic.json", "r01_ncu_traffic.json"):
+        path = os.path.join(ROOT, "profiles", name)
+        if not os.path.exists(path):
+            continue
+        with open(path) as f:
+            table = json.load(f)["bytes_per_launch"]
+        vals = [val for key, val in table.items() if kernel in key]
+        if vals:
+            return vals[-1]
     return None
 
 
