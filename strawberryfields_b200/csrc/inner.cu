@@ -34,6 +34,8 @@
 //
 // Replaces, for these geometries, the same reference sites as apply.cu:
 // Circuit.apply_gate_BLAS (fockbackend/circuit.py:118-217) and apply_twomode_gate (219-365).
+#include <cuda.h>  // CUtensorMap and its enums (types only: the encoder is fetched through the runtime)
+
 #include "tasks.cuh"
 #include "tma.cuh"
 
@@ -61,6 +63,8 @@ struct InnerPlan {
   int gran, r;              // padding granule (slices) and r = 8 / gcd(row_ss mod 8, 8) of the lane map
   int wide;                 // 1: granules of 32 slices, the lane map spreads a warp over 8/r of them
   int teams;                // consumer teams launched (1 or 2, at most in_teams(D))
+  int use_tmap;             // rows mode: one tensor-map copy per tile and direction instead of D row copies
+  int box_units;            // rows mode + tensor map: 128-byte units of a row chunk (box dim 1)
   int sk, sl;               // staged element strides of gate index 1 / 2 inside a slice
   int rows, row_pitch;      // rows mode: D rows, staged row pitch in elements
   int chunks_per_outer;     // rows mode: ceil(mid / slices_per_tile)
@@ -108,9 +112,24 @@ __device__ __forceinline__ void row_copy(const InnerPlan& p, cplx* gp, unsigned 
 // the bulk copies of one tile: LOAD global -> stage (arming the stage's mbarrier), else stage -> global
 template <bool LOAD>
 __device__ __forceinline__ void tile_copy(const InnerPlan& p, const Geometry& g, cplx* base, unsigned long long t,
-                                          unsigned stage_smem, unsigned bar, int lane) {
+                                          unsigned stage_smem, unsigned bar, int lane, const CUtensorMap* tmap,
+                                          int batch) {
   const int nsl = tile_slices(p, g, t);
   int turn = 0;
+  if (p.use_tmap) {
+    // tensor [batch][outer * D rows][row run in 128-byte units][16 doubles]; box = [1][D][box_units][16]
+    if (lane == 0) {
+      const unsigned long long o = t / (unsigned)p.chunks_per_outer;
+      const int c = (int)(t % (unsigned)p.chunks_per_outer);
+      if (LOAD) {
+        mbar_expect_tx(bar, (unsigned)p.box_units * 128u * (unsigned)p.rows);  // the whole box, zero fill included
+        tensor_load_4d(stage_smem, tmap, 0, c * p.box_units, (int)(o * (unsigned)p.rows), batch, bar);
+      } else {
+        tensor_store_4d(tmap, 0, c * p.box_units, (int)(o * (unsigned)p.rows), batch, stage_smem);
+      }
+    }
+    return;
+  }
   if (LOAD) {
     // the expected byte count is armed before any lane's copy can complete
     if (lane == 0) mbar_expect_tx(bar, (unsigned)nsl * (unsigned)p.slice_elems * 16u);
@@ -136,7 +155,8 @@ __device__ __forceinline__ void tile_copy(const InnerPlan& p, const Geometry& g,
 template <int D, int TEAMS>
 __global__ void __launch_bounds__(in_threads(TEAMS), 1)
 k_apply_inner_tma(cplx* __restrict__ state, const cplx* __restrict__ coef, const Geometry g, const TaskTable tt,
-                  const InnerPlan p, unsigned long long n_tiles /* over all batch entries */) {
+                  const InnerPlan p, unsigned long long n_tiles /* over all batch entries */,
+                  const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long full_bar[IN_MAX_STAGES], done_bar[IN_MAX_STAGES], free_bar[IN_MAX_STAGES];
   cplx* tiles = reinterpret_cast<cplx*>(smem_raw);
@@ -162,11 +182,13 @@ k_apply_inner_tma(cplx* __restrict__ state, const cplx* __restrict__ coef, const
 
   if (warp >= IN_TEAM * TEAMS) {
     // ---------------- DMA warps: a loader and a storer, their 32 lanes share a tile's copies ---------
+    int batch = 0;
     auto where = [&](unsigned long long i, cplx*& base, unsigned long long& t) {
       const unsigned long long gt = t_lo + i;
       const unsigned long long b = gt / p.tiles_per_state;
       t = gt - b * p.tiles_per_state;
       base = state + (size_t)b * g.state_batch_stride;
+      batch = (int)b;
     };
     cplx* base;
     unsigned long long t;
@@ -175,7 +197,8 @@ k_apply_inner_tma(cplx* __restrict__ state, const cplx* __restrict__ coef, const
         const unsigned st = (unsigned)(i % S);
         if (i >= S) mbar_wait(smem_u32(&free_bar[st]), (unsigned)(((i / S) - 1) & 1));  // tile i-S has left the stage
         where(i, base, t);
-        tile_copy<true>(p, g, base, t, smem_u32(tiles + (size_t)st * p.tile_elems), smem_u32(&full_bar[st]), lane);
+        tile_copy<true>(p, g, base, t, smem_u32(tiles + (size_t)st * p.tile_elems), smem_u32(&full_bar[st]), lane, &tmap,
+                        batch);
       }
     } else {
       for (unsigned long long i = 0; i < n_my; ++i) {
@@ -183,7 +206,7 @@ k_apply_inner_tma(cplx* __restrict__ state, const cplx* __restrict__ coef, const
         mbar_wait(smem_u32(&done_bar[st]), (unsigned)((i / S) & 1));  // consumers are done with tile i
         fence_async_smem();
         where(i, base, t);
-        tile_copy<false>(p, g, base, t, smem_u32(tiles + (size_t)st * p.tile_elems), 0, lane);
+        tile_copy<false>(p, g, base, t, smem_u32(tiles + (size_t)st * p.tile_elems), 0, lane, &tmap, batch);
         bulk_commit();  // every lane commits its own (possibly empty) group per tile
         if (i >= 1) {
           bulk_wait_read<1>();  // this lane's stores of tile i-1 have read the stage
@@ -252,7 +275,8 @@ k_apply_inner_tma(cplx* __restrict__ state, const cplx* __restrict__ coef, const
 
 template <int D, int TEAMS>
 static cudaError_t launch_dt(cplx* state, const cplx* coef, const Geometry& g, const TaskTable& tt,
-                             const InnerPlan& p, unsigned long long n_tiles, size_t smem, cudaStream_t st) {
+                             const InnerPlan& p, unsigned long long n_tiles, size_t smem, cudaStream_t st,
+                             const CUtensorMap& tmap) {
   static int sms = 0;
   if (sms == 0) {
     int dev = 0;
@@ -263,17 +287,52 @@ static cudaError_t launch_dt(cplx* state, const cplx* coef, const Geometry& g, c
       cudaFuncSetAttribute(k_apply_inner_tma<D, TEAMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const unsigned grid = (unsigned)(n_tiles < (unsigned long long)sms ? n_tiles : (unsigned long long)sms);
-  k_apply_inner_tma<D, TEAMS><<<grid, in_threads(TEAMS), smem, st>>>(state, coef, g, tt, p, n_tiles);
+  k_apply_inner_tma<D, TEAMS><<<grid, in_threads(TEAMS), smem, st>>>(state, coef, g, tt, p, n_tiles, tmap);
   return cudaSuccess;
 }
 
 template <int D>
 static cudaError_t launch_d(cplx* state, const cplx* coef, const Geometry& g, const TaskTable& tt,
-                            const InnerPlan& p, unsigned long long n_tiles, size_t smem, cudaStream_t st) {
+                            const InnerPlan& p, unsigned long long n_tiles, size_t smem, cudaStream_t st,
+                            const CUtensorMap& tmap) {
   if constexpr (in_teams(D) == 2) {
-    if (p.teams == 2) return launch_dt<D, 2>(state, coef, g, tt, p, n_tiles, smem, st);
+    if (p.teams == 2) return launch_dt<D, 2>(state, coef, g, tt, p, n_tiles, smem, st, tmap);
   }
-  return launch_dt<D, 1>(state, coef, g, tt, p, n_tiles, smem, st);
+  return launch_dt<D, 1>(state, coef, g, tt, p, n_tiles, smem, st, tmap);
+}
+
+// cuTensorMapEncodeTiled through the runtime (no link against libcuda)
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static encode_tiled_fn tensor_map_encoder() {
+  static encode_tiled_fn fn = [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      ptr = nullptr;
+    return (encode_tiled_fn)ptr;
+  }();
+  return fn;
+}
+
+// rows geometry as a tensor of doubles [batch][outer * D rows][row run / 128 B][16]: the D rows of a tile are ONE box
+static bool rows_tensor_map(CUtensorMap* tm, cplx* state, int D, const Geometry& g, long long hi, int nbatch,
+                            int box_units) {
+  encode_tiled_fn enc = tensor_map_encoder();
+  if (!enc || (hi * 2) % 16 != 0 || box_units > 256 || D > 256) return false;
+  const unsigned long long rows_total = (unsigned long long)(g.n_slices / g.mid) * (unsigned long long)D;
+  cuuint64_t dims[4] = {16, (cuuint64_t)(hi * 2 / 16), (cuuint64_t)rows_total, (cuuint64_t)nbatch};
+  cuuint64_t strides[3] = {128, (cuuint64_t)hi * 16,
+                           (cuuint64_t)(nbatch > 1 ? g.state_batch_stride : (long long)rows_total * hi) * 16};
+  cuuint32_t box[4] = {16, (cuuint32_t)box_units, (cuuint32_t)D, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  if (dims[1] >= (1ull << 32) || dims[2] >= (1ull << 32) || strides[1] >= (1ull << 40) || strides[2] >= (1ull << 40))
+    return false;
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, state, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) ==
+         CUDA_SUCCESS;
 }
 
 static int gcd_int(int a, int b) { return b == 0 ? a : gcd_int(b, a % b); }
@@ -284,6 +343,8 @@ bool launch_inner_tma(int D, cplx* state, const cplx* coef, const Geometry& g, c
   const bool pair = g.stride2 != 0;
   InnerPlan p;
   memset(&p, 0, sizeof(p));
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
   const int group_bytes = 32 * D * D * 16;                 // one lane group of a pair gate
   int q = IN_TILE_TARGET / group_bytes;
   if (q < 1) q = 1;
@@ -342,6 +403,16 @@ bool launch_inner_tma(int D, cplx* state, const cplx* coef, const Geometry& g, c
         p.gran = 0;
         p.r = 8;
       }
+      // One tensor-map copy per tile and direction instead of D row copies (each bulk operation costs ~40 ns
+      // of tile time): chunks of exactly 32 * q slices, the tail of a row run is clipped by the
+      // tensor bounds (zero fill on load, skipped on store).  B200_INNER_ROWS=bulk keeps the row copies.
+      if (!(rows_mode && (rows_mode[0] == 'b' || rows_mode[0] == 'p')) && p.gran == 0 &&
+          rows_tensor_map(&tmap, state, D, g, hi, nbatch, 32 * q * D * 2 / 16)) {
+        p.use_tmap = 1;
+        p.slices_per_tile = 32 * q;
+        p.chunks_per_outer = (int)((mid + p.slices_per_tile - 1) / p.slices_per_tile);
+        p.box_units = p.slices_per_tile * D * 2 / 16;
+      }
       p.row_pitch = p.slices_per_tile * D + (p.gran ? p.slices_per_tile / p.gran : 0);
       p.hi_stride = hi;
       p.block_slices = p.slices_per_tile;
@@ -395,7 +466,7 @@ bool launch_inner_tma(int D, cplx* state, const cplx* coef, const Geometry& g, c
   cudaError_t e = cudaSuccess;
 #define B200_LAUNCH(N) \
   case N:              \
-    e = launch_d<N>(state, coef, g, tt, p, n_tiles, smem, st); \
+    e = launch_d<N>(state, coef, g, tt, p, n_tiles, smem, st, tmap); \
     break;
   switch (D) {
     B200_LAUNCH(2) B200_LAUNCH(3) B200_LAUNCH(4) B200_LAUNCH(5) B200_LAUNCH(6) B200_LAUNCH(7) B200_LAUNCH(8)

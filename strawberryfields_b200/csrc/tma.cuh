@@ -43,6 +43,23 @@ __device__ __forceinline__ void bulk_wait_read() {
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
+// tensor-map copies: ONE operation moves a whole 4-D box (cp.async.bulk.tensor, SASS UTMALDG / UTMASTG); the
+// CUtensorMap lives in kernel parameter space (__grid_constant__).  Out-of-bounds parts of a box are zero-filled
+// on load and skipped on store.
+__device__ __forceinline__ void tensor_load_4d(unsigned dst_smem, const void* tmap, int c0, int c1, int c2, int c3,
+                                               unsigned bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];\n" ::
+          "r"(dst_smem),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tensor_store_4d(const void* tmap, int c0, int c1, int c2, int c3, unsigned src_smem) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3, %4}], [%5];\n" ::"l"(tmap),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(src_smem)
+               : "memory");
+}
+
 __device__ __forceinline__ void mbar_arrive(unsigned bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
 }
