@@ -153,86 +153,6 @@ k_apply_inner(cplx* __restrict__ state, const cplx* __restrict__ coef, const Geo
   }
 }
 
-// Persistent, 4-stage version of the staged kernel (unbatched launches): one CTA per SM walks over
-// its stages of `spc` slices; three stages of cp.async copies (~150 KB per SM) are always in flight
-// while the fourth is being computed, which is what keeps HBM busy -- the one-shot kernel above has
-// at most one stage per CTA in flight and measured 3.97 TB/s.
-constexpr int INNER_STAGES = 4;
-template <int D>
-__global__ void __launch_bounds__(inner_threads(D), 1)
-k_apply_inner_pipe(cplx* __restrict__ state, const cplx* __restrict__ coef, const Geometry g, const TaskTable tt,
-                   int rows, int spc, unsigned nstages_total) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  cplx* M = reinterpret_cast<cplx*>(smem_raw);
-  const int nthr = inner_threads(D), tid = threadIdx.x;
-  const int SL = (rows * D) | 1;
-  cplx* bufs = M + g.coef_count;
-  const int buf_elems = spc * SL;
-  const long long row_stride = g.stride1 > g.stride2 ? g.stride1 : g.stride2;
-  for (int i = tid; i < g.coef_count; i += nthr) {
-    cplx v = coef[i];
-    if (g.conj) v.y = -v.y;
-    M[i] = v;
-  }
-
-  auto issue = [&](unsigned stage, int slot) {
-    if (stage < nstages_total) {
-      cplx* tile = bufs + (size_t)slot * buf_elems;
-      const unsigned s0 = stage * (unsigned)spc;
-      for (int idx = tid; idx < spc * D; idx += nthr) {
-        const int sg = idx / D, l = idx - sg * D;
-        const unsigned s = s0 + sg;
-        if (s < g.n_slices) {
-          const unsigned i_mid = s % g.mid, i_out = s / g.mid;
-          const cplx* src = state + (long long)i_out * g.outer_step + (long long)i_mid * g.mid_step + l;
-          cplx* dst = tile + sg * SL + l;
-          for (int k = 0; k < rows; ++k) cp_async16_(dst + k * D, src + (long long)k * row_stride);
-        }
-      }
-    }
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
-  };
-
-  const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
-  const int sk = rows == 1 ? 1 : (g.stride1 > g.stride2 ? D : 1);
-  const int sl = rows == 1 ? 0 : (g.stride1 > g.stride2 ? 1 : D);
-  const long long step = sk + tt.dl * sl;
-  const int ngroups = spc / 32;
-
-  unsigned stage = blockIdx.x;
-  for (int p = 0; p < INNER_STAGES - 1; ++p) issue(stage + (unsigned)p * gridDim.x, p);
-  for (int it = 0; stage < nstages_total; stage += gridDim.x, ++it) {
-    const int slot = it % INNER_STAGES;
-    issue(stage + (unsigned)(INNER_STAGES - 1) * gridDim.x, (it + INNER_STAGES - 1) % INNER_STAGES);
-    asm volatile("cp.async.wait_group 3;\n" ::: "memory");  // INNER_STAGES - 1 younger groups may be pending
-    __syncthreads();
-    cplx* tile = bufs + (size_t)slot * buf_elems;
-    const unsigned s0 = stage * (unsigned)spc;
-    for (int wt = warp; wt < ngroups * tt.ntasks; wt += nwarps) {
-      const int gi = wt / tt.ntasks, task = wt - gi * tt.ntasks;
-      const int sg = gi * 32 + lane;
-      if (s0 + sg < g.n_slices) {
-        cplx* ps = tile + sg * SL;
-        const SubBlock sb0 = tt.sub[task][0], sb1 = tt.sub[task][1];
-        task_dispatch<D>(sb0.c, ps + sb0.start_k * sk + sb0.start_l * sl, ps + sb1.start_k * sk + sb1.start_l * sl,
-                         step, M + sb0.coef, M + sb1.coef);
-      }
-    }
-    __syncthreads();
-    for (int idx = tid; idx < spc * D; idx += nthr) {
-      const int sg = idx / D, l = idx - sg * D;
-      const unsigned s = s0 + sg;
-      if (s < g.n_slices) {
-        const unsigned i_mid = s % g.mid, i_out = s / g.mid;
-        cplx* dst = state + (long long)i_out * g.outer_step + (long long)i_mid * g.mid_step + l;
-        const cplx* src = tile + sg * SL + l;
-        for (int k = 0; k < rows; ++k) dst[(long long)k * row_stride] = src[k * D];
-      }
-    }
-    __syncthreads();  // the slot is refilled by the next iteration's prefetch
-  }
-}
-
 // ---- diagonal gates ---------------------------------------------------------------------
 // Index arithmetic is 32-bit whenever the state has fewer than 2^32 elements (always true for
 // one launch on one GPU: 180 GB / 16 B = 1.1e10 would need it, 1e9-1e10-element shards do not).
@@ -340,29 +260,6 @@ static cudaError_t launch_inner_d(cplx* state, const cplx* coef, const Geometry&
                                   int nbatch, cudaStream_t st) {
   const int spc = rows == 1 ? inner_threads(D) : 32;  // slices per CTA: one per thread / one lane group
   const int SL = (rows * D) | 1;
-  // Persistent 4-stage pipeline (unbatched launches, four stages must fit in shared memory).  Measured
-  // on B200 at D = 10: 3.7-3.9 TB/s against 3.97 TB/s for the one-shot kernel below -- the staged compute,
-  // not the bytes in flight, is the limit -- so it is off unless B200_INNER_PIPE=1 (kept for round 2).
-  static const bool pipe_on = [] {
-    const char* v = getenv("B200_INNER_PIPE");
-    return v && v[0] == '1';
-  }();
-  size_t smem_pipe = ((size_t)g.coef_count + (size_t)INNER_STAGES * spc * SL) * sizeof(cplx);
-  if (pipe_on && nbatch == 1 && smem_pipe <= 227 * 1024) {
-    static int sms = 0;
-    if (sms == 0) {
-      int dev = 0;
-      cudaGetDevice(&dev);
-      if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-    }
-    cudaError_t e = cudaFuncSetAttribute(k_apply_inner_pipe<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem_pipe);
-    if (e != cudaSuccess) return e;
-    unsigned nst = (g.n_slices + spc - 1) / spc;
-    unsigned gx = nst < (unsigned)sms ? nst : (unsigned)sms;
-    k_apply_inner_pipe<D><<<gx, inner_threads(D), smem_pipe, st>>>(state, coef, g, tt, rows, spc, nst);
-    return cudaSuccess;
-  }
   size_t smem = ((size_t)g.coef_count + (size_t)spc * SL) * sizeof(cplx);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(k_apply_inner<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

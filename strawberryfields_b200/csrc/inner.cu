@@ -36,6 +36,9 @@
 // Circuit.apply_gate_BLAS (fockbackend/circuit.py:118-217) and apply_twomode_gate (219-365).
 #include <cuda.h>  // CUtensorMap and its enums (types only: the encoder is fetched through the runtime)
 
+#include <map>
+#include <vector>
+
 #include "tasks.cuh"
 #include "tma.cuh"
 
@@ -61,10 +64,12 @@ struct InnerPlan {
   //                                     + s / gran   (one pad word per granule of `gran` slices; gran = 0: none)
   int block_slices, block_elems, row_ss;
   int gran, r;              // padding granule (slices) and r = 8 / gcd(row_ss mod 8, 8) of the lane map
-  int wide;                 // 1: granules of 32 slices, the lane map spreads a warp over 8/r of them
   int teams;                // consumer teams launched (1 or 2, at most in_teams(D))
-  int use_tmap;             // rows mode: one tensor-map copy per tile and direction instead of D row copies
-  int box_units;            // rows mode + tensor map: 128-byte units of a row chunk (box dim 1)
+  int use_tmap;             // 1: rows geometry, ONE 4-D box per tile; 2: contiguous tile, `boxes` 3-D boxes
+  int box_units;            // 128-byte units of a box (box dim 1)
+  int boxes;                // use_tmap == 2: boxes per tile (<= 256 units each)
+  int swz;                  // the tensor map stages with SWIZZLE_128B: element word c lives at c ^ ((c >> 3) & 7)
+  unsigned char lane_map[32];  // swz: slice (inside a group of 32) owned by each lane, conflict free by search
   int sk, sl;               // staged element strides of gate index 1 / 2 inside a slice
   int rows, row_pitch;      // rows mode: D rows, staged row pitch in elements
   int chunks_per_outer;     // rows mode: ceil(mid / slices_per_tile)
@@ -116,7 +121,7 @@ __device__ __forceinline__ void tile_copy(const InnerPlan& p, const Geometry& g,
                                           int batch) {
   const int nsl = tile_slices(p, g, t);
   int turn = 0;
-  if (p.use_tmap) {
+  if (p.use_tmap == 1) {
     // tensor [batch][outer * D rows][row run in 128-byte units][16 doubles]; box = [1][D][box_units][16]
     if (lane == 0) {
       const unsigned long long o = t / (unsigned)p.chunks_per_outer;
@@ -126,6 +131,23 @@ __device__ __forceinline__ void tile_copy(const InnerPlan& p, const Geometry& g,
         tensor_load_4d(stage_smem, tmap, 0, c * p.box_units, (int)(o * (unsigned)p.rows), batch, bar);
       } else {
         tensor_store_4d(tmap, 0, c * p.box_units, (int)(o * (unsigned)p.rows), batch, stage_smem);
+      }
+    }
+    return;
+  }
+  if (p.use_tmap == 2) {
+    // contiguous tile: tensor [batch][1][state in 128-byte units][16 doubles], `boxes` boxes of box_units units;
+    // boxes that start behind the end of the state are not issued, one that straddles it is clipped
+    if (lane == 0) {
+      const long long u0 = (long long)t * p.boxes * p.box_units;
+      const long long total_units = (long long)g.n_slices * p.slice_elems / 8;
+      int nb = 0;
+      for (int b = 0; b < p.boxes; ++b) nb += (u0 + (long long)b * p.box_units < total_units) ? 1 : 0;
+      if (LOAD) mbar_expect_tx(bar, (unsigned)nb * (unsigned)p.box_units * 128u);
+      for (int b = 0; b < nb; ++b) {
+        const unsigned sa = stage_smem + (unsigned)b * (unsigned)p.box_units * 128u;
+        if (LOAD) tensor_load_4d(sa, tmap, 0, (int)(u0 + (long long)b * p.box_units), 0, batch, bar);
+        else tensor_store_4d(tmap, 0, (int)(u0 + (long long)b * p.box_units), 0, batch, sa);
       }
     }
     return;
@@ -149,6 +171,82 @@ __device__ __forceinline__ void tile_copy(const InnerPlan& p, const Geometry& g,
   }
 }
 
+// ---- tasks on a SWIZZLE_128B stage ---------------------------------------------------------------------
+// The tensor-map copies stage a tile densely but with the hardware's 128-byte swizzle: 16-byte word c of the
+// stage is stored at c ^ ((c >> 3) & 7) (stage bases are 1024-byte aligned).  With the right lane -> slice map
+// (searched on the host, InnerPlan::lane_map) the eight lanes of a quarter warp then hit eight different bank
+// groups although their slices are an even number of words apart -- conflict free WITHOUT padding, so a tile is
+// still one or two bulk operations.
+__device__ __forceinline__ cplx* swz_at(cplx* base, int c) { return base + (c ^ ((c >> 3) & 7)); }
+
+template <int C>
+__device__ __forceinline__ void rows_apply_swz(cplx* __restrict__ base, int i0, int step, const cplx* __restrict__ M,
+                                               const cplx (&x)[C]) {
+#pragma unroll 1
+  for (int a = 0; a + 1 < C; a += 2) {
+    double axx = 0.0, ayy = 0.0, axy = 0.0, ayx = 0.0;
+    double bxx = 0.0, byy = 0.0, bxy = 0.0, byx = 0.0;
+    const cplx* __restrict__ Ma = M + a * C;
+    const cplx* __restrict__ Mb = Ma + C;
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      const cplx ma = Ma[j], mb = Mb[j], v = x[j];
+      axx = fma(ma.x, v.x, axx);
+      ayy = fma(ma.y, v.y, ayy);
+      axy = fma(ma.x, v.y, axy);
+      ayx = fma(ma.y, v.x, ayx);
+      bxx = fma(mb.x, v.x, bxx);
+      byy = fma(mb.y, v.y, byy);
+      bxy = fma(mb.x, v.y, bxy);
+      byx = fma(mb.y, v.x, byx);
+    }
+    *swz_at(base, i0 + a * step) = make_double2(axx - ayy, axy + ayx);
+    *swz_at(base, i0 + (a + 1) * step) = make_double2(bxx - byy, bxy + byx);
+  }
+  if (C & 1) {
+    double axx = 0.0, ayy = 0.0, axy = 0.0, ayx = 0.0;
+    const cplx* __restrict__ Ma = M + (C - 1) * C;
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      const cplx ma = Ma[j], v = x[j];
+      axx = fma(ma.x, v.x, axx);
+      ayy = fma(ma.y, v.y, ayy);
+      axy = fma(ma.x, v.y, axy);
+      ayx = fma(ma.y, v.x, ayx);
+    }
+    *swz_at(base, i0 + (C - 1) * step) = make_double2(axx - ayy, axy + ayx);
+  }
+}
+
+template <int C0, int C1>
+__device__ __forceinline__ void task_apply_swz(cplx* __restrict__ base, int i0, int i1, int step,
+                                               const cplx* __restrict__ M0, const cplx* __restrict__ M1) {
+  cplx x0[C0];
+  cplx x1[C1 > 0 ? C1 : 1];
+#pragma unroll
+  for (int j = 0; j < C0; ++j) x0[j] = *swz_at(base, i0 + j * step);
+#pragma unroll
+  for (int j = 0; j < C1; ++j) x1[j] = *swz_at(base, i1 + j * step);
+  rows_apply_swz<C0>(base, i0, step, M0, x0);
+  if constexpr (C1 > 0) rows_apply_swz<C1>(base, i1, step, M1, x1);
+}
+
+template <int D>
+__device__ __forceinline__ void task_dispatch_swz(int c0, cplx* base, int i0, int i1, int step, const cplx* M0,
+                                                  const cplx* M1) {
+#define B200_CASE(N) \
+  case N:            \
+    if constexpr (N <= D) task_apply_swz<N, D - N>(base, i0, i1, step, M0, M1); \
+    break;
+  switch (c0) {
+    B200_CASE(1) B200_CASE(2) B200_CASE(3) B200_CASE(4) B200_CASE(5) B200_CASE(6) B200_CASE(7) B200_CASE(8)
+    B200_CASE(9) B200_CASE(10) B200_CASE(11) B200_CASE(12) B200_CASE(13) B200_CASE(14) B200_CASE(15)
+    B200_CASE(16)
+    default: break;
+  }
+#undef B200_CASE
+}
+
 // TEAMS is a template parameter because it sets the register budget: one team (384 threads) compiles to
 // ~133 registers, two teams (704 threads) are capped at 80 -- running one team under the 80-register cap
 // cost the pair-gate kernel a quarter of its rate (4.6 against 5.8-6.1 TB/s).
@@ -157,7 +255,7 @@ __global__ void __launch_bounds__(in_threads(TEAMS), 1)
 k_apply_inner_tma(cplx* __restrict__ state, const cplx* __restrict__ coef, const Geometry g, const TaskTable tt,
                   const InnerPlan p, unsigned long long n_tiles /* over all batch entries */,
                   const __grid_constant__ CUtensorMap tmap) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  extern __shared__ __align__(1024) unsigned char smem_raw[];  // swizzled stages need 1024-byte alignment
   __shared__ __align__(8) unsigned long long full_bar[IN_MAX_STAGES], done_bar[IN_MAX_STAGES], free_bar[IN_MAX_STAGES];
   cplx* tiles = reinterpret_cast<cplx*>(smem_raw);
   cplx* M = tiles + (size_t)p.stages * p.tile_elems;
@@ -225,15 +323,12 @@ k_apply_inner_tma(cplx* __restrict__ state, const cplx* __restrict__ coef, const
   const long long step = p.sk + tt.dl * p.sl;
   const int n_wt = p.groups * tt.ntasks;
   // conflict-free lane -> slice map inside a group of 32 slices (identity when no padding is needed)
-  // gran = 4r: lane l of a group takes slice 4r * (x mod w) + x / w + r * (l / 8), x = l mod 8, w = 8 / r.
-  // wide (gran = 32, one-mode gates: fewer, larger bulk copies): w consecutive groups form a super-group;
-  // its h-th warp-task takes, from granule (x mod w), slice 4r * h + x / w + r * (l / 8).
-  int lane_slice = lane;
-  const int lw = p.gran > 0 ? 8 / p.r : 1;
+  // padded granules (gran = 4r): lane l of a group takes slice 4r * (x mod w) + x / w + r * (l / 8), x = l mod 8,
+  // w = 8 / r; swizzled stages: the searched map; else the identity
+  int lane_slice = p.swz ? (int)p.lane_map[lane] : lane;
   if (p.gran > 0) {
-    const int x = lane & 7;
-    lane_slice = p.wide ? 32 * (x % lw) + x / lw + p.r * (lane >> 3)
-                        : 4 * p.r * (x % lw) + x / lw + p.r * (lane >> 3);
+    const int x = lane & 7, lw = 8 / p.r;
+    lane_slice = 4 * p.r * (x % lw) + x / lw + p.r * (lane >> 3);
   }
   long long cur_batch = -1;
   for (unsigned long long i = team; i < n_my; i += TEAMS) {
@@ -258,13 +353,19 @@ k_apply_inner_tma(cplx* __restrict__ state, const cplx* __restrict__ coef, const
     const int nsl = tile_slices(p, g, t);
     for (int wt = wteam; wt < n_wt; wt += IN_TEAM) {
       const int gi = wt / tt.ntasks, task = wt - gi * tt.ntasks;
-      const int sg = p.wide ? (gi / lw) * lw * 32 + 4 * p.r * (gi % lw) + lane_slice : gi * 32 + lane_slice;
+      const int sg = gi * 32 + lane_slice;
       if (sg < nsl) {
-        cplx* ps = tile + (sg / p.block_slices) * p.block_elems + (sg % p.block_slices) * p.row_ss +
-                   (p.gran > 0 ? sg / p.gran : 0);
+        const int org = (sg / p.block_slices) * p.block_elems + (sg % p.block_slices) * p.row_ss +
+                        (p.gran > 0 ? sg / p.gran : 0);
         const SubBlock sb0 = tt.sub[task][0], sb1 = tt.sub[task][1];
-        task_dispatch<D>(sb0.c, ps + sb0.start_k * p.sk + sb0.start_l * p.sl,
-                         ps + sb1.start_k * p.sk + sb1.start_l * p.sl, step, Mt + sb0.coef, Mt + sb1.coef);
+        if (p.swz) {
+          task_dispatch_swz<D>(sb0.c, tile, org + sb0.start_k * p.sk + sb0.start_l * p.sl,
+                               org + sb1.start_k * p.sk + sb1.start_l * p.sl, (int)step, Mt + sb0.coef, Mt + sb1.coef);
+        } else {
+          cplx* ps = tile + org;
+          task_dispatch<D>(sb0.c, ps + sb0.start_k * p.sk + sb0.start_l * p.sl,
+                           ps + sb1.start_k * p.sk + sb1.start_l * p.sl, step, Mt + sb0.coef, Mt + sb1.coef);
+        }
       }
     }
     fence_async_smem();  // generic-proxy writes to the stage become visible to the bulk store
@@ -319,7 +420,7 @@ static encode_tiled_fn tensor_map_encoder() {
 
 // rows geometry as a tensor of doubles [batch][outer * D rows][row run / 128 B][16]: the D rows of a tile are ONE box
 static bool rows_tensor_map(CUtensorMap* tm, cplx* state, int D, const Geometry& g, long long hi, int nbatch,
-                            int box_units) {
+                            int box_units, bool swizzle) {
   encode_tiled_fn enc = tensor_map_encoder();
   if (!enc || (hi * 2) % 16 != 0 || box_units > 256 || D > 256) return false;
   const unsigned long long rows_total = (unsigned long long)(g.n_slices / g.mid) * (unsigned long long)D;
@@ -331,8 +432,84 @@ static bool rows_tensor_map(CUtensorMap* tm, cplx* state, int D, const Geometry&
   if (dims[1] >= (1ull << 32) || dims[2] >= (1ull << 32) || strides[1] >= (1ull << 40) || strides[2] >= (1ull << 40))
     return false;
   return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, state, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) ==
-         CUDA_SUCCESS;
+             swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// a state (per batch entry) as a tensor of doubles [batch][1][state / 128 B][16]: contiguous tiles are boxes of
+// box_units units
+static bool flat_tensor_map(CUtensorMap* tm, cplx* state, long long state_elems, long long batch_stride, int nbatch,
+                            int box_units, bool swizzle) {
+  encode_tiled_fn enc = tensor_map_encoder();
+  if (!enc || state_elems % 8 != 0 || box_units > 256 || box_units < 1) return false;
+  cuuint64_t dims[4] = {16, (cuuint64_t)(state_elems / 8), 1, (cuuint64_t)nbatch};
+  cuuint64_t strides[3] = {128, (cuuint64_t)state_elems * 16,
+                           (cuuint64_t)(nbatch > 1 ? batch_stride : state_elems) * 16};
+  cuuint32_t box[4] = {16, (cuuint32_t)box_units, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  if (dims[1] >= (1ull << 32) || strides[1] >= (1ull << 40) || strides[2] >= (1ull << 40)) return false;
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, state, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// Lane -> slice map for a swizzled stage: among the maps slice = (a * x + b * q) mod 32 (x = lane mod 8,
+// q = lane / 8) that are bijections, the one with the fewest bank-group collisions inside a quarter warp,
+// over every element offset a task touches.  Pure host arithmetic, cached per geometry.
+static int swizzled_lane_map(const InnerPlan& p, int D, bool pair, unsigned char* out) {
+  struct Key {
+    int D, bs, be, ss, sk, sl, pair;
+    bool operator<(const Key& o) const {
+      return memcmp(this, &o, sizeof(Key)) < 0;
+    }
+  };
+  struct Val {
+    unsigned char map[32];
+    int worst;
+  };
+  static std::map<Key, Val> cache;
+  Key key{D, p.block_slices, p.block_elems, p.row_ss, p.sk, p.sl, pair ? 1 : 0};
+  auto it = cache.find(key);
+  if (it == cache.end()) {
+    std::vector<int> offs;
+    if (pair) {
+      for (int k = 0; k < D; ++k)
+        for (int l = 0; l < D; ++l) offs.push_back(k * (p.sk > p.sl ? p.sk : p.sl) + l);
+    } else {
+      for (int l = 0; l < D; ++l) offs.push_back(l);
+    }
+    auto origin = [&](int sg) { return (sg / p.block_slices) * p.block_elems + (sg % p.block_slices) * p.row_ss; };
+    Val best;
+    best.worst = 1 << 30;
+    for (int a = 1; a < 32; ++a)
+      for (int b = 1; b < 32; ++b) {
+        unsigned char m[32];
+        unsigned seen = 0;
+        for (int lane = 0; lane < 32; ++lane) {
+          m[lane] = (unsigned char)((a * (lane & 7) + b * (lane >> 3)) & 31);
+          seen |= 1u << m[lane];
+        }
+        if (seen != 0xffffffffu) continue;
+        int worst = 0;
+        for (int gi = 0; gi < p.groups && gi < 4; ++gi)
+          for (int q = 0; q < 4; ++q)
+            for (int off : offs) {
+              int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+              for (int x = 0; x < 8; ++x) {
+                const int c = origin(gi * 32 + m[q * 8 + x]) + off;
+                const int w = ++cnt[(c ^ (c >> 3)) & 7];
+                if (w > worst) worst = w;
+              }
+            }
+        if (worst < best.worst) {
+          best.worst = worst;
+          memcpy(best.map, m, 32);
+        }
+      }
+    it = cache.emplace(key, best).first;
+  }
+  memcpy(out, it->second.map, 32);
+  return it->second.worst;
 }
 
 static int gcd_int(int a, int b) { return b == 0 ? a : gcd_int(b, a % b); }
@@ -345,6 +522,17 @@ bool launch_inner_tma(int D, cplx* state, const cplx* coef, const Geometry& g, c
   memset(&p, 0, sizeof(p));
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
+  // Tensor-map copies (tools/inner_probe.py, D = 10, TB/s; bulk row / granule copies in brackets):
+  //   rows geometry, plain box            5.25   [4.4-4.8]   with SWIZZLE_128B + searched lane map 5.21-5.28
+  //   one-mode gate, swizzled boxes       5.24   [5.0-5.3 unpadded, 2-way conflicts]
+  //   adjacent pairs, swizzled boxes      4.93   [5.64 padded granules: the swizzle's address arithmetic costs more
+  //                                               than the two extra bulk copies]
+  // Default: plain box for rows, swizzled boxes for one-mode gates, padded granules for adjacent pairs.
+  // B200_INNER_TMAP = 0: bulk copies only; "swizzle": swizzled tensor maps wherever they apply.
+  static const char* tm_env = getenv("B200_INNER_TMAP");
+  const bool want_tmap = !(tm_env && tm_env[0] == '0');
+  const bool swizzle_all = want_tmap && tm_env && tm_env[0] == 's';
+  const bool want_swizzle = want_tmap && (swizzle_all || !pair);
   const int group_bytes = 32 * D * D * 16;                 // one lane group of a pair gate
   int q = IN_TILE_TARGET / group_bytes;
   if (q < 1) q = 1;
@@ -360,21 +548,12 @@ bool launch_inner_tma(int D, cplx* state, const cplx* coef, const Geometry& g, c
     p.block_slices = p.slices_per_tile;
     p.block_elems = 0;
     p.row_ss = D;
-    pad_plan(D);
-    // wide granules (32 slices per bulk copy instead of 4r) when the groups of a tile pair up; B200_INNER_ONE
-    // = "narrow" / "flat" select the 4r granules / the unpadded layout (measurement switches)
-    // Measured (B200, D = 10, profiles/r02_inner_kernel.md): the one-mode tile is ONE contiguous 51 KB run, and
-    // every extra bulk copy costs more than the bank conflicts it removes -- unpadded ("flat", 4 copies of
-    // <= 16 KB, 2-way conflicts) 5.2 TB/s, granules of 32 slices ("wide", 10 copies) 4.4, of 4r ("narrow", 20
-    // copies) 3.7.  B200_INNER_ONE = wide / narrow select the padded layouts.
-    static const char* one_mode = getenv("B200_INNER_ONE");
-    if (one_mode && one_mode[0] == 'w' && p.gran > 0 && p.groups % (8 / p.r) == 0) {
-      p.wide = 1;
-      p.gran = 32;
-    } else if (!(one_mode && one_mode[0] == 'n')) {
-      p.gran = 0;
-      p.r = 8;
-    }
+    // Measured (B200, D = 10): the one-mode tile is ONE contiguous 51 KB run, and every extra bulk copy costs
+    // more than the bank conflicts it removes -- unpadded (4 copies of <= 16 KB, 2-way conflicts) 5.0-5.3 TB/s,
+    // granules of 32 slices (10 copies) 4.4, of 16 (20 copies) 3.7.  The tile stays unpadded; the swizzled
+    // tensor-map boxes below make it conflict free without more copies.
+    p.gran = 0;
+    p.r = 8;
     p.sk = 1;
     p.sl = 0;
     p.tile_elems = p.slices_per_tile * D + (p.gran ? p.slices_per_tile / p.gran : 0);
@@ -395,20 +574,19 @@ bool launch_inner_tma(int D, cplx* state, const cplx* coef, const Geometry& g, c
       p.row_ss = D;
       // Measured (tools/inner_probe.py, D = 10): padding the rows (two granules of 16 slices per row, 20 + 20
       // bulk copies per tile) gives 3.5 TB/s, unpadded rows (10 + 10 copies, 2-way bank conflicts) 4.8 TB/s:
-      // rows stay unpadded.  B200_INNER_ROWS=pad selects the padded layout.
+      // rows stay unpadded.
       static const char* rows_mode = getenv("B200_INNER_ROWS");
-      if (rows_mode && rows_mode[0] == 'p' && p.slices_per_tile % 32 == 0) {
-        pad_plan(D);
-      } else {
-        p.gran = 0;
-        p.r = 8;
-      }
+      p.gran = 0;
+      p.r = 8;
       // One tensor-map copy per tile and direction instead of D row copies (each bulk operation costs ~40 ns
       // of tile time): chunks of exactly 32 * q slices, the tail of a row run is clipped by the
       // tensor bounds (zero fill on load, skipped on store).  B200_INNER_ROWS=bulk keeps the row copies.
-      if (!(rows_mode && (rows_mode[0] == 'b' || rows_mode[0] == 'p')) && p.gran == 0 &&
-          rows_tensor_map(&tmap, state, D, g, hi, nbatch, 32 * q * D * 2 / 16)) {
+      // With SWIZZLE_128B (rows of a multiple of 1024 bytes) the stage is conflict free as well.
+      const bool rows_swz = swizzle_all && (32 * q * D * 16) % 1024 == 0;
+      if (!(rows_mode && rows_mode[0] == 'b') && want_tmap &&
+          rows_tensor_map(&tmap, state, D, g, hi, nbatch, 32 * q * D * 2 / 16, rows_swz)) {
         p.use_tmap = 1;
+        p.swz = rows_swz ? 1 : 0;
         p.slices_per_tile = 32 * q;
         p.chunks_per_outer = (int)((mid + p.slices_per_tile - 1) / p.slices_per_tile);
         p.box_units = p.slices_per_tile * D * 2 / 16;
@@ -448,6 +626,32 @@ bool launch_inner_tma(int D, cplx* state, const cplx* coef, const Geometry& g, c
     p.sk = g.stride1 > g.stride2 ? hi_staged : 1;
     p.sl = g.stride1 > g.stride2 ? 1 : hi_staged;
   }
+  // Contiguous tiles (one-mode gates, adjacent pairs, short-mid blocks that fit one box) through a tensor map with
+  // SWIZZLE_128B: unpadded, one or two bulk operations per tile, and conflict free with the searched lane map.
+  if (want_swizzle && !p.rows_mode && D % 2 == 0) {
+    const int flat_elems = pair && p.block_elems ? (p.slices_per_tile / p.block_slices) * p.block_elems
+                                                 : p.slices_per_tile * p.slice_elems;
+    const long long state_elems = (long long)g.n_slices * p.slice_elems;
+    if (flat_elems % 8 == 0) {
+      const int units = flat_elems / 8;
+      int boxes = (units + 255) / 256;
+      while (boxes <= 8 && (units % boxes != 0 || (boxes > 1 && (units / boxes) % 8 != 0))) ++boxes;
+      if (boxes <= 8 && flat_tensor_map(&tmap, state, state_elems, g.state_batch_stride, nbatch, units / boxes, true)) {
+        p.use_tmap = 2;
+        p.swz = 1;
+        p.boxes = boxes;
+        p.box_units = units / boxes;
+        p.gran = 0;
+        p.r = 8;
+        p.tile_elems = flat_elems;
+      }
+    }
+  }
+  if (p.swz) {
+    swizzled_lane_map(p, D, pair, p.lane_map);
+  } else {
+    for (int l = 0; l < 32; ++l) p.lane_map[l] = (unsigned char)l;
+  }
   // Two consumer teams for the dense one-mode task (400 DFMA per warp-task: one team was compute-latency
   // bound, 3.7-4.9 TB/s); one team for pair gates, where a second team would take the ring stage that keeps
   // a second tile of loads in flight (measured 5.2-5.5 against 5.8-6.1 TB/s).  B200_INNER_TEAMS overrides.
@@ -455,7 +659,8 @@ bool launch_inner_tma(int D, cplx* state, const cplx* coef, const Geometry& g, c
   p.teams = pair ? 1 : 2;
   if (teams_env && (teams_env[0] == '1' || teams_env[0] == '2')) p.teams = teams_env[0] - '0';
   if (p.teams > in_teams(D)) p.teams = in_teams(D);
-  const size_t tile_bytes = (((size_t)p.tile_elems * 16) + 127) / 128 * 128;
+  const size_t tile_align = p.swz ? 1024 : 128;
+  const size_t tile_bytes = (((size_t)p.tile_elems * 16) + tile_align - 1) / tile_align * tile_align;
   p.tile_elems = (int)(tile_bytes / 16);
   const size_t coef_bytes = (size_t)g.coef_count * 16 * p.teams;  // one copy of the table per team
   if (coef_bytes + 3 * tile_bytes > (size_t)IN_SMEM_LIMIT) return false;  // fewer than three stages: not worth it
