@@ -3,8 +3,9 @@
 achieved HBM GB/s).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
-                    [--workload c1|c2|c3|c4] [--modes M] [--fuse fold|tile|off] [--exchange auto|p2p|nccl]
-                    [--from-vacuum]
+                    [--workload c1|c2|c3|c4] [--modes M] [--fuse fold|tile|off]
+                    [--exchange auto|p2p|push|nccl] [--exchange-overlap G] [--from-vacuum]
+                    [--no-parity] [--no-ten-mode] [--no-cpu-baseline]
 
 Workload (N = 1): BASELINE config 2 -- 8-mode pure state, cutoff 10 (1e8 complex128
 amplitudes, 1.6 GB), Sgate + Dgate on every mode and a random 8-mode rectangular
@@ -14,18 +15,24 @@ through one gate of the call list (fused or not), so a step is 80 x 1e8 updates.
 Under torchrun (N > 1) the workload is BASELINE config 5: ONE 9-mode state (1e9 amplitudes)
 sharded over the N GPUs ("scaling": "strong"; `--modes 10` gives the 160 GB state on 8 GPUs).
 `--workload c1|c3|c4` run the other BASELINE configs on one GPU (boson sampling, mixed state +
-loss, batched QNN layer).
+loss + MeasureFock, batched QNN layer).
 
 * ``value``: updates/s with the state resident in HBM, CUDA-event timed, max over ranks.
-* ``e2e``: the same metric through the reference-facing plugin API (``B200FockBackend``:
-  ``begin_circuit`` .. gate calls .. ``state()``) with host buffers: every step copies the
-  step's gate-parameter table from pinned host memory to the device and reads the
+* ``e2e``: the same metric through the reference-facing plugin API with its default options
+  (``B200FockBackend``: ``reset`` .. gate calls .. ``state()``) and host buffers: every step
+  copies the step's gate-parameter table from pinned host memory to the device and reads the
   requested result (trace + a list of Fock probabilities) back to the host.
 * ``roofline``: the dominant kernel (k_apply_blocks) -- algorithmic bytes (32 B per
-  amplitude per pass) / CUDA-event time per launch, against MEASURED_PEAKS.json.
-* ``cpu_baseline``: the oracle port in the reference's loop structure
-  (oracle/fock_oracle.py, style="reference") on a bounded sample of the same workload.
-* ``--impl reference``: the reference arm -- the same oracle port timed on the host cores.
+  amplitude per pass) / CUDA-event time per launch, against MEASURED_PEAKS.json; ``by_pass``
+  gives every pass family, ``hbm_GBps_per_gpu_whole_step`` the whole step.
+* ``cpu_baseline`` / ``--impl reference``: the UNMODIFIED reference fock backend (oracle/_ref,
+  installed by oracle/build_ref.py) on the host cores, on a full-size gate prefix of the same
+  workload (one BSgate / the first S + D + R + BS of the circuit); the oracle port on a reduced
+  size only if oracle/_ref is missing.
+* multi-rank lines additionally carry ``parity`` (single-photon transfer on the sharded state,
+  the sharded state against an unsharded run of the same circuit on rank 0, a seeded
+  MeasureFock), ``single_gpu_same_workload_ms`` + ``strong_efficiency``, ``exchange`` (NVLink
+  GB/s per direction) and, at N = 8, ``ten_mode`` (the 10-mode / 160 GB state).
 """
 from __future__ import annotations
 

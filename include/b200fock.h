@@ -201,6 +201,17 @@ int b200_norm2(const b200_c128* psi_dev, int64_t n, double* out_dev, double* par
 int b200_scale(b200_c128* dev, int64_t n, double re, double im, const double* divisor_dev,
                int sqrt_div, void* stream);
 
+/* ---- single-mode reduced density matrix / photon-number marginal of a ket in ONE read of the state
+ *      (reference: backend.py:219-253, states.py:613-642, circuit.py:675-677 -- einsum / tensordot on the host).
+ * The state is viewed as [outer, D, inner] along the kept mode's axis.  diag_only = 0: out_dev receives the
+ * Hermitian D x D matrix rho[a][b] = sum_r psi[.., a, ..] conj(psi[.., b, ..]) (b200_c128, [nbatch][D][D]);
+ * diag_only = 1: the marginal probabilities (double, [nbatch][D]).  part_dev: scratch of
+ * b200_gram1_part_doubles(D, nbatch) doubles.  Deterministic (fixed reduction order).  Cutoffs 1..12 (matrix),
+ * 1..16 (marginal).                                                                                          */
+int64_t b200_gram1_part_doubles(int D, int nbatch);
+int b200_gram1(const b200_c128* psi_dev, int64_t outer, int D, int64_t inner, int diag_only, void* out_dev,
+               double* part_dev, int nbatch, int64_t state_batch_stride, void* stream);
+
 /* ---- multi-GPU axis exchange (the reference has no distributed path) ------------
  * One launch performs a rank's whole share of the all-to-all that swaps the sharded leading
  * axes of the state with local ones.  For every source s the copy is

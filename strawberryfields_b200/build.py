@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200fock.so")
-SOURCES = ["api.cu", "gates_gen.cu", "apply.cu", "tile.cu", "generic.cu", "exchange.cu", "inner.cu"]
+SOURCES = ["api.cu", "gates_gen.cu", "apply.cu", "tile.cu", "generic.cu", "exchange.cu", "inner.cu", "gram.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -239,6 +239,7 @@ class DeviceCircuit:
         snap._inactive = set()
         snap._scratch = None
         snap._part = None
+        snap._gram_part = None
         snap._norm_part = torch.zeros(4096, dtype=torch.float64, device=self.device)
         snap._shared = True
         self._shared = True
@@ -1252,6 +1253,8 @@ class DeviceCircuit:
         self._flush()
         n, D, B = self._num_modes, self._trunc, self._B
         k = len(keep)
+        if self._pure and k == 1 and D <= L.MAX_FAST_CUTOFF and n > 1:
+            return self._gram1(keep[0], diag_only=True)
         out = torch.empty(B * D ** k, dtype=torch.float64, device=self.device)
         per = self._size()
         if self._pure:
@@ -1276,6 +1279,8 @@ class DeviceCircuit:
             return self._partial_trace_keep(keep).view(self._B, -1)
         n, D, B = self._num_modes, self._trunc, self._B
         k = len(keep)
+        if k == 1 and D <= L.GRAM_MAX_CUTOFF and n > 1:
+            return self._gram1(keep[0], diag_only=False)
         per, new_per = D ** n, D ** (2 * k)
         out = self._new(B * new_per)
         oa = [(B, per, per, new_per)] if B > 1 else []
@@ -1284,6 +1289,23 @@ class DeviceCircuit:
             oa.append((D, 0, self._stride(m), D ** (2 * k - 2 - 2 * j)))
         red = [(D, self._stride(m), self._stride(m)) for m in range(n) if m not in keep]
         self._gather(self._buf, self._buf, out, oa, red, flags=L.FLAG_CONJ_B)
+        return out.view(B, -1)
+
+    def _gram1(self, mode, diag_only):
+        """Reduced density matrix (complex128 [B, D*D]) or photon-number marginal (float64 [B, D]) of ONE mode of
+        a ket, in one read of the state (``b200_gram1``): what homodyne measurement, ``mean_photon``,
+        ``quad_expectation`` and ``wigner`` reduce to."""
+        D, B = self._trunc, self._B
+        inner = self._stride(mode)
+        per = self._size()
+        out = (torch.empty(B * D, dtype=torch.float64, device=self.device) if diag_only
+               else self._new(B * D * D))
+        need = int(L.load().b200_gram1_part_doubles(D, B))
+        part = self.__dict__.get("_gram_part")
+        if part is None or part.numel() < need:
+            part = self._gram_part = torch.empty(need, dtype=torch.float64, device=self.device)
+        L.call("b200_gram1", _ptr(self._buf), per // (D * inner), D, inner, 1 if diag_only else 0, _ptr(out), _ptr(part),
+               B, per, self._stream())
         return out.view(B, -1)
 
     def product_overlap_device(self, vectors):

@@ -17,6 +17,7 @@ MAX_AXES = 24
 MAX_CUTOFF = 64        # single-mode and diagonal gates, reductions
 MAX_PAIR_CUTOFF = 27   # two-mode gates / loss channel: the packed table must fit 227 KB of shared memory
 MAX_BATCH = 65535      # the batch axis is gridDim.z
+GRAM_MAX_CUTOFF = 12    # b200_gram1 keeps D (D + 1) accumulators in registers
 
 # gate kinds / rules (mirror include/b200fock.h)
 GATE_DISPLACEMENT, GATE_SQUEEZE = 1, 2
@@ -123,6 +124,8 @@ SIGNATURES = {
     "b200_abs2": [_P, _P, _L, _P],
     "b200_norm2": [_P, _L, _P, _P, _P],
     "b200_scale": [_P, _L, _D, _D, _P, _I, _P],
+    "b200_gram1_part_doubles": [_I, _I],
+    "b200_gram1": [_P, _L, _I, _L, _I, _P, _P, _I, _L, _P],
     "b200_exchange_copy": [C.POINTER(XchgDesc), _I, _I, _P],
     "b200_peer_barrier": [C.POINTER(PeerFlags), C.c_uint64, _D, _P],
 }
@@ -131,6 +134,7 @@ _RESTYPES = {
     "b200_packed_size": C.c_int64,
     "b200_launch_count": C.c_int64,
     "b200_tile_smem_bytes": C.c_int64,
+    "b200_gram1_part_doubles": C.c_int64,
     "b200_reset_launch_count": None,
 }
 

@@ -396,3 +396,19 @@ class FakeLib:
 
     def b200_peer_barrier(self, pf, epoch, timeout_s, stream):
         raise AssertionError("the CPU double synchronises with the process group, not with device flags")
+
+    # -- single-mode Gram matrix / marginal
+    def b200_gram1_part_doubles(self, D, nbatch):
+        return nbatch * 444 * D * (D + 1)
+
+    def b200_gram1(self, psi, outer, D, inner, diag_only, out, part, nb, sbs, stream):
+        assert D <= (16 if diag_only else 12)
+        for b in range(nb):
+            v = _c(_addr(psi) + 16 * b * sbs, outer * D * inner).reshape(outer, D, inner)
+            rho = np.einsum("oai,obi->ab", v, v.conj())
+            if diag_only:
+                _d(_addr(out) + 8 * b * D, D)[:] = np.real(np.diag(rho))
+            else:
+                _c(_addr(out) + 16 * b * D * D, D * D)[:] = rho.reshape(-1)
+        self.launches += 2
+        return 0

@@ -245,3 +245,27 @@ def test_config3_full_size_matches_oracle_fixture(lazy):
     post = be.state()
     assert abs(post.trace() - complex(ref["post_trace"]).real) < TOL
     assert abs(post.fock_prob([0] * n) - float(np.real(ref["post_prob_of_outcome"]))) < TOL
+
+
+@pytest.mark.parametrize("lazy", [False, True], ids=["eager", "lazy"])
+def test_config5_full_size_matches_oracle_fixture(lazy):
+    """BASELINE config 5's state on ONE GPU (9 modes, cutoff 10, 1e9 amplitudes, 99 gates) against the oracle's
+    run of the same circuit (tests/golden/ref_config5_full.npz: 40 minutes of numpy in the build container).  The
+    sharded runs are compared with this unsharded state inside bench.py (`parity` in every multi-GPU line)."""
+    import torch
+
+    ref = _golden("ref_config5_full.npz")
+    n, D = int(ref["n_modes"]), int(ref["cutoff"])
+    if torch.cuda.get_device_properties(0).total_memory < 60e9:
+        pytest.skip("needs a GPU with >= 60 GB")
+    calls = W.config2_circuit(n, seed=42)
+    assert len(calls) == int(ref["gates"])
+    be = _backend(n=n, cutoff_dim=D, lazy_vacuum=lazy)
+    W.run_calls(be, calls)
+    st = be.state()
+    assert np.abs(_sampled_entries(st._view, ref["idx"]) - ref["amp"]).max() < TOL
+    assert abs(st.trace() - float(ref["trace"])) < 1e-11
+    marg = np.stack([st._view.marginal_probs_device([m])[0].cpu().numpy() for m in range(n)])
+    assert np.abs(marg - ref["marg"]).max() < 1e-11   # sums of 1e8 probabilities
+    del st, be
+    torch.cuda.empty_cache()

@@ -422,3 +422,32 @@ def test_diag_multi_geometries(lib, torch_mod):
              _p(_dev(torch, tabs.reshape(-1))), B, D ** n, 2 * D, None)
     want = psi * tabs[:, 0].reshape(B, D, 1, 1, 1) * tabs[:, 1].conj().reshape(B, 1, 1, D, 1)
     assert np.abs(st.cpu().numpy().reshape(psi.shape) - want).max() < TOL * 10
+
+
+@pytest.mark.parametrize("D,n", [(2, 5), (5, 4), (10, 4), (12, 3), (16, 3), (7, 2)])
+def test_gram1_every_axis(lib, torch_mod, D, n):
+    """b200_gram1: reduced density matrix / marginal of one mode of a ket in one read of the state, every axis
+    position, full matrix (cutoffs <= 12) and diagonal (<= 16), and a batch"""
+    torch = torch_mod
+    rs = np.random.RandomState(D * 10 + n)
+    B = 3
+    psi = _rand(rs, B, *([D] * n))
+    st = _dev(torch, psi.reshape(-1))
+    part = torch.empty(int(lib.load().b200_gram1_part_doubles(D, B)), dtype=torch.float64, device="cuda")
+    letters = "abcdefgh"[:n]
+    for axis in range(n):
+        inner = D ** (n - 1 - axis)
+        sub_in = "z" + letters
+        sub_cj = "z" + letters.replace(letters[axis], "X")
+        want = np.einsum("%s,%s->z%sX" % (sub_in, sub_cj, letters[axis]), psi, psi.conj())
+        probs = torch.empty(B * D, dtype=torch.float64, device="cuda")
+        lib.call("b200_gram1", _p(st), D ** axis, D, inner, 1, _p(probs), _p(part), B, D ** n, None)
+        assert np.abs(probs.cpu().numpy().reshape(B, D) - np.real(np.einsum("zaa->za", want))).max() < 1e-10
+        if D <= 12:
+            rho = torch.empty(B * D * D, dtype=torch.complex128, device="cuda")
+            lib.call("b200_gram1", _p(st), D ** axis, D, inner, 0, _p(rho), _p(part), B, D ** n, None)
+            assert np.abs(rho.cpu().numpy().reshape(B, D, D) - want).max() < 1e-10
+    if D > 12:
+        with pytest.raises(lib.B200Error):
+            rho = torch.empty(B * D * D, dtype=torch.complex128, device="cuda")
+            lib.call("b200_gram1", _p(st), 1, D, D ** (n - 1), 0, _p(rho), _p(part), B, D ** n, None)
