@@ -15,17 +15,21 @@ a gate on modes stored there is a purely local launch of the single-GPU kernels.
 
 Exchange.  A gate on a mode stored on a sharded axis first swaps ALL g sharded axes with g
 local ones in one all-to-all (each rank keeps 1/P of its shard and sends (P-1)/P of it --
-cheaper per mode than g pairwise half-shard swaps): pack (strided gather) ->
-``all_to_all_single`` (NCCL over NVLink / NVSwitch) -> unpack (strided gather).  Which
-logical mode lives on which physical axis is tracked on the host; nothing is swapped back.
+cheaper per mode than g pairwise half-shard swaps).  With the ranks' buffers mapped into each
+other (CUDA IPC over NVLink / NVSwitch) it is a device-side barrier kernel plus one launch of
+``b200_exchange_copy`` per part of the new shard -- bulk-copy-engine pulls straight from the
+peers' HBM, no staging, no host synchronisation -- overlapped with the first gates behind it
+(``_exchange_p2p``); without peer mapping: pack (strided gather) -> ``all_to_all_single``
+(NCCL) -> unpack (``_exchange_nccl``).  Which logical mode lives on which physical axis is
+tracked on the host; nothing is swapped back.
 
 Scheduling.  Gates are queued (as in the single-GPU lazy queue) and, at a flush, executed
 in dependency order preferring gates whose modes are local; when every runnable gate needs
 a sharded mode an exchange brings the sharded modes in.  Which local modes it evicts -- and,
 while the state is still the vacuum, which modes start out sharded -- is decided by
 ``exchange_plan.plan``: a bounded search seeded with the online farthest-next-use (Belady)
-rule.  The 9- and 10-mode interferometer circuits need 2 exchanges on 2 or 4 ranks and 3
-on 8 ranks.
+rule, with costs that grow when an exchange would move short contiguous runs.  The 9- and
+10-mode interferometer circuits need 2 exchanges on 2 or 4 ranks and 3 on 8 ranks.
 """
 from __future__ import annotations
 

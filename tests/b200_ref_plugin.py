@@ -40,8 +40,8 @@ class B200AsFock(plugin.B200FockBackend):
     def begin_circuit(self, num_subsystems, **kwargs):
         kwargs.pop("batch_size", None)        # the reference fock backend ignores it
         kwargs.setdefault("strict_purity", True)  # reproduce the reference's pure/mixed representation (F7)
-        if os.environ.get("B200_REF_SUITE_LAZY") == "1":  # run the same suite with the lazy-vacuum option
-            kwargs.setdefault("lazy_vacuum", True)
+        # the plugin default (lazy vacuum + deferred program); B200_REF_SUITE_LAZY=0 runs the eager path
+        kwargs.setdefault("lazy_vacuum", os.environ.get("B200_REF_SUITE_LAZY", "1") != "0")
         return super().begin_circuit(num_subsystems, **kwargs)
 
 
