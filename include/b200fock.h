@@ -189,6 +189,12 @@ int b200_gather_reduce(const b200_gather_desc* desc, const void* A_dev, const b2
                        void* C_dev, int flags, b200_c128* part_dev, void* stream);
 
 /* ---- elementwise helpers --------------------------------------------------------------- */
+/* out[b][j][i] = f[b][j] * in[b][i], 0 <= j < nf, 0 <= i < n_in: a product factor (|0> under its pending
+ * single-mode operator: nf = D; a rank-one (ket, bra) factor of a density matrix: nf = D * D) becomes the new
+ * outermost axis of the tensor -- the lazy vacuum's replacement for np.tensordot / the reference's full-size
+ * allocation at begin_circuit (circuit.py:89-116).  f_batch_stride = 0: one factor for every batch entry.     */
+int b200_outer_axis(const b200_c128* in_dev, const b200_c128* f_dev, b200_c128* out_dev, int64_t n_in, int nf,
+                    int nbatch, int64_t in_batch_stride, int64_t f_batch_stride, void* stream);
 int b200_fill_zero(b200_c128* dev, int64_t n, void* stream);
 int b200_set_element(b200_c128* dev, int64_t index, double re, double im, void* stream);
 /* probs[i] = |psi[i]|^2  -- states.py:596-598 */

@@ -725,15 +725,17 @@ class DeviceCircuit:
             old_per = self._size()
             if self._pure:
                 f, new_per = v, old_per * D
-                oa = [(D, 0, 1, old_per)]
             else:
                 # conj_physical: the kernel reads raw memory, torch's lazy conjugate bit would be lost
                 f = (v.reshape(nb, D, 1) * torch.conj_physical(v).reshape(nb, 1, D)).contiguous()
                 new_per = old_per * D * D
-                oa = [(D, 0, D, D * old_per), (D, 0, 1, old_per)]
             out = self._new(B * new_per)
-            lead = [(B, old_per, f[0].numel() if nb > 1 else 0, new_per)] if B > 1 else []
-            self._gather(self._buf, f, out, lead + oa + [(old_per, 1, 0, 1)])
+            # out[b][j][i] = f[b][j] * tensor[b][i]: one coalesced read, nf coalesced writes (b200_outer_axis)
+            nf = f[0].numel()
+            if self._buf.numel() < B * old_per or f.numel() < nb * nf:
+                raise L.B200Error("outer_axis operands are smaller than the launch")
+            L.call("b200_outer_axis", _ptr(self._buf), _ptr(f.contiguous()), _ptr(out), old_per, nf, B, old_per,
+                   nf if nb > 1 else 0, self._stream())
             self._buf, self._shared, self._scratch = out, False, None
             self._inactive.discard(m)
             self._phys = list(self._mode_axes(m)) + self._phys

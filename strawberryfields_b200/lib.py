@@ -119,6 +119,7 @@ SIGNATURES = {
     "b200_tile_smem_bytes": [_I, _L],
     "b200_apply_tile_pass": [_P, _L, _I, _L, _L, C.POINTER(TileOp), _I, C.POINTER(C.c_int), _P, _L, _I, _L, _L, _P],
     "b200_gather_reduce": [C.POINTER(GatherDesc), _P, _P, _P, _I, _P, _P],
+    "b200_outer_axis": [_P, _P, _P, _L, _I, _I, _L, _L, _P],
     "b200_fill_zero": [_P, _L, _P],
     "b200_set_element": [_P, _L, _D, _D, _P],
     "b200_abs2": [_P, _P, _L, _P],

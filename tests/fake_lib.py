@@ -412,3 +412,11 @@ class FakeLib:
                 _c(_addr(out) + 16 * b * D * D, D * D)[:] = rho.reshape(-1)
         self.launches += 2
         return 0
+
+    def b200_outer_axis(self, inp, f, out, n_in, nf, nb, in_bs, f_bs, stream):
+        for b in range(nb):
+            v = _c(_addr(inp) + 16 * b * in_bs, n_in)
+            fac = _c(_addr(f) + 16 * b * f_bs, nf)
+            _c(_addr(out) + 16 * b * n_in * nf, n_in * nf)[:] = np.multiply.outer(fac, v).reshape(-1)
+        self.launches += 1
+        return 0

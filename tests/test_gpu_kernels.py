@@ -451,3 +451,18 @@ def test_gram1_every_axis(lib, torch_mod, D, n):
         with pytest.raises(lib.B200Error):
             rho = torch.empty(B * D * D, dtype=torch.complex128, device="cuda")
             lib.call("b200_gram1", _p(st), 1, D, D ** (n - 1), 0, _p(rho), _p(part), B, D ** n, None)
+
+
+def test_outer_axis(lib, torch_mod):
+    """b200_outer_axis: out[b][j][i] = f[b][j] * in[b][i] (odd and even lengths, shared and per-entry factors)"""
+    torch = torch_mod
+    rs = np.random.RandomState(41)
+    for n_in, nf, B, shared in ((1, 10, 1, True), (7, 5, 3, False), (1000, 100, 2, True), (4097, 10, 1, True),
+                                (10 ** 5, 10, 2, False)):
+        x = _rand(rs, B, n_in)
+        f = _rand(rs, 1 if shared else B, nf)
+        out = torch.empty(B * nf * n_in, dtype=torch.complex128, device="cuda")
+        xd, fd = _dev(torch, x.reshape(-1)), _dev(torch, f.reshape(-1))   # keep both alive across the launch
+        lib.call("b200_outer_axis", _p(xd), _p(fd), _p(out), n_in, nf, B, n_in, 0 if shared else nf, None)
+        want = np.einsum("bj,bi->bji", np.broadcast_to(f, (B, nf)), x)
+        assert np.abs(out.cpu().numpy().reshape(B, nf, n_in) - want).max() < 1e-14
