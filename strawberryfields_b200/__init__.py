@@ -17,7 +17,7 @@ from .circuit import DeviceCircuit, DeviceParams  # noqa: F401
 from .states import B200FockState  # noqa: F401
 from . import io  # noqa: F401  (Blackbird / XIR program I/O, state checkpoints)
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"
 
 try:  # make sf.Engine("b200fock") work as soon as the package is imported next to SF
     register()

@@ -354,6 +354,9 @@ class DeviceCircuit:
         return torch.from_numpy(dev).to(self.device) if isinstance(dev, np.ndarray) else dev
 
     def _gen1(self, kind, p0, p1):
+        ahead = self._pregenerated(kind, p0)
+        if ahead is not None:
+            return ahead
         nb, sc, dev, key = self._params(p0, p1)
         D = self._trunc
 
@@ -365,6 +368,9 @@ class DeviceCircuit:
         return TABLES.get(None if key is None else self._key("g1", kind, key), build)
 
     def _gen_diag(self, kind, p0):
+        ahead = self._pregenerated(kind, p0)
+        if ahead is not None:
+            return ahead
         nb, sc, dev, key = self._params(p0)
         D = self._trunc
         per = D * D if kind == L.DIAG_CROSS_KERR else D
@@ -377,6 +383,9 @@ class DeviceCircuit:
         return TABLES.get(None if key is None else self._key("gd", kind, key), build)
 
     def _gen2(self, kind, p0, p1=0.0):
+        ahead = self._pregenerated(kind, p0)
+        if ahead is not None:
+            return ahead
         nb, sc, dev, key = self._params(p0, p1)
         D = self._trunc
         if D > L.MAX_PAIR_CUTOFF:
@@ -632,8 +641,60 @@ class DeviceCircuit:
                     first.setdefault(m, i)
         if count:
             self._inner_hint = min(count, key=lambda m: (count[m], first[m]))
+        self._pregenerate(log)
+        try:
+            for name, args in log:
+                getattr(self, name)(*args)
+        finally:
+            self._pregen = {}
+
+    # gate method -> (generator entry point, kind, table entries as a function of the cutoff)
+    _GENERATORS = {
+        "displacement": ("b200_gen_gate1", L.GATE_DISPLACEMENT, lambda D: D * D),
+        "squeeze": ("b200_gen_gate1", L.GATE_SQUEEZE, lambda D: D * D),
+        "phase_shift": ("b200_gen_diag", L.DIAG_ROTATION, lambda D: D),
+        "kerr_interaction": ("b200_gen_diag", L.DIAG_KERR, lambda D: D),
+        "cross_kerr_interaction": ("b200_gen_diag", L.DIAG_CROSS_KERR, lambda D: D * D),
+        "beamsplitter": ("b200_gen_gate2", L.GATE_BEAMSPLITTER, L.packed_size),
+        "mzgate": ("b200_gen_gate2", L.GATE_MZ, L.packed_size),
+        "two_mode_squeeze": ("b200_gen_gate2", L.GATE_S2, L.packed_size),
+    }
+
+    def _pregenerate(self, log):
+        """Gate tables of device-resident parameters (``DeviceParams``: no recipe, so the table cache cannot
+        serve them) are generated in ONE launch per gate kind for the whole recorded program -- the generators
+        take a batch of parameter pairs -- instead of one launch per gate while the tensors are still small and
+        the host is the bottleneck."""
+        self._pregen = {}
+        D = self._trunc
+        groups = {}
         for name, args in log:
-            getattr(self, name)(*args)
+            if name in self._GENERATORS and args and isinstance(args[0], DeviceParams) and args[0].nbatch == 1:
+                groups.setdefault(name, []).append(args[0])
+        for name, dps in groups.items():
+            if len(dps) < 2 or (D > L.MAX_PAIR_CUTOFF and self._GENERATORS[name][0] == "b200_gen_gate2"):
+                continue
+            entry, kind, size = self._GENERATORS[name]
+            per, K = size(D), len(dps)
+            params = torch.stack([dp.tensor for dp in dps], dim=1).contiguous()   # [2, K]
+            out = self._new(K * per)
+            if entry == "b200_gen_diag":
+                L.call(entry, kind, D, K, 0.0, _ptr(params), _ptr(out), self._stream())
+            else:
+                L.call(entry, kind, D, K, 0.0, 0.0, _ptr(params), _ptr(out), self._stream())
+            shape = (1, D, D) if entry == "b200_gen_gate1" else (1, per)
+            for k, dp in enumerate(dps):
+                self._pregen.setdefault((id(dp), kind), []).append(out[k * per:(k + 1) * per].view(shape))
+
+    def _pregenerated(self, kind, p0):
+        """the table generated ahead for this DeviceParams object, if any (each is handed out once)"""
+        if isinstance(p0, DeviceParams):
+            tabs = self.__dict__.get("_pregen", {}).get((id(p0), kind))
+            if tabs:
+                t = tabs.pop(0)
+                t._recipe = None
+                return t
+        return None
 
     # ------------------------------------------------------------------ lazy queue
     def _touch(self, *modes):

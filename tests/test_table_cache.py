@@ -141,3 +141,37 @@ def test_batched_vacuum_and_norm_use_one_launch_each(counting):
     tr = be.state().trace()
     assert counting.calls["b200_norm2"] == 0 and counting.calls["b200_gather_reduce"] >= 1
     assert np.allclose(tr, 1.0, atol=1e-3) and np.shape(tr) == (6,)
+
+
+def test_device_params_tables_are_generated_in_batches_at_replay(counting):
+    """Deferred program + DeviceParams (no recipe: the cache cannot serve them): one generator launch per gate
+    KIND for the whole recorded program instead of one per gate; same state as with host parameters."""
+    import torch
+
+    from strawberryfields_b200 import DeviceParams
+    from strawberryfields_b200 import workloads as W
+    from strawberryfields_b200.backend import B200FockBackend
+
+    n, D = 4, 5
+    calls = W.config2_circuit(n, seed=9) + [("kerr_interaction", 0.2, 1), ("two_mode_squeeze", 0.1, 0.4, 0, 3)]
+    ref = B200FockBackend()
+    ref.begin_circuit(n, cutoff_dim=D)
+    W.run_calls(ref, calls)
+    want = ref.state().ket().copy()
+
+    be = B200FockBackend()
+    be.begin_circuit(n, cutoff_dim=D)          # lazy vacuum: gate calls are recorded
+    two = ("squeeze", "displacement", "beamsplitter", "mzgate", "two_mode_squeeze")
+    counting.calls.clear()
+    for c in calls:
+        vals = [float(x) for x in c[1:] if not isinstance(x, int)] + [0.0]
+        modes = [x for x in c[1:] if isinstance(x, int)]
+        dp = DeviceParams(torch.tensor(vals[:2], dtype=torch.float64))
+        getattr(be, c[0])(*([dp] + ([None] if c[0] in two else []) + modes))
+    assert sum(counting.calls[k] for k in ("b200_gen_gate1", "b200_gen_gate2", "b200_gen_diag")) == 0  # recorded only
+    got = be.state().ket()
+    assert np.abs(got - want).max() < 1e-12
+    # S, D -> 2 launches of gen_gate1; R (+ the single K) -> gen_diag; BS (+ the single S2) -> gen_gate2
+    assert counting.calls["b200_gen_gate1"] == 2
+    assert counting.calls["b200_gen_diag"] == 2      # one batch of rotations + the lone Kerr gate
+    assert counting.calls["b200_gen_gate2"] == 2     # one batch of beamsplitters + the lone S2 gate

@@ -62,7 +62,7 @@ def main():
         "ms_per_training_step": dt * 1e3, "gates": gates, "stored_elements": elements,
         "forward_equivalent_updates_per_s": gates * elements / dt,
         "kernel_launches_per_step": int(handle.b200_launch_count()) // args.steps,
-        "loss": float(loss), "peak_memory_GB": torch.cuda.max_memory_allocated() / 1e9,
+        "loss": float(loss.detach()), "peak_memory_GB": torch.cuda.max_memory_allocated() / 1e9,
     }))
 
 
