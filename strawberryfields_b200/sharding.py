@@ -94,6 +94,13 @@ class ShardedCircuit(DeviceCircuit):
         # of 43.9 ms per circuit)
         self._overlap_ops = int(opts.pop("exchange_overlap", 4))
         self._xstream = None
+        # CTAs that drive NVLink in b200_exchange_copy (0: the library default, 32).  One peer is saturated by 32
+        # (tools/xchg_probe.py) and on 4 GPUs 32 and 48 give the same circuit time (77.3 / 77.6 ms); with 7 peers
+        # interleaved 48 measured 618-647 GB/s against 539-561 (and 516 against 550 ms for the 10-mode circuit).
+        import os
+
+        env = os.environ.get("B200_EXCHANGE_CTAS")
+        self.exchange_ctas = int(env) if env else (48 if self._world >= 8 else 0)
         opts.pop("batch_size", None)
         opts["fuse"] = "fold"
         # lazy vacuum, sharded flavour: the part of a fresh program that fits one GPU runs REPLICATED on
