@@ -9,8 +9,10 @@ the parts of both languages a Fock-backend program uses:
 
 * Blackbird: ``name`` / ``version`` / ``target dev (opt = val)`` header, scalar and array variable
   declarations (``float x = 0.3``, ``complex array U[4, 4] =`` + indented rows), comments, and operation
-  lines ``Op(args, key=val) | modes``.  ``for`` loops, templates (``{par}``) and measured parameters
-  (``q0``) are refused with ``NotImplementedError``.
+  lines ``Op(args, key=val) | modes``, and ``for <type> <var> in start:stop[:step]`` / ``in [..]`` loops over
+  an indented block of operations (unrolled; the variable may appear in arguments, array subscripts and
+  mode lists).  Templates (``{par}``), ``type`` / ``include`` statements and measured parameters (``q0``) are
+  refused with ``NotImplementedError``.
 * XIR: ``options: .. end;`` and ``constants: .. end;`` blocks, ``use`` / declaration statements (ignored),
   and statements ``Op(args, key: val) | [wires];``.
 
@@ -140,20 +142,26 @@ def _parse_args(text, env, kw_sep):
     return args, kwargs
 
 
-def _parse_modes(text):
+def _parse_modes(text, env=None):
     text = text.strip()
     if text and text[0] in "[(":
         if text[-1] not in "])":
             raise ProgramSyntaxError("unbalanced mode list %r" % text)
         text = text[1:-1]
     modes = []
-    for tok in text.split(","):
+    for tok in _split_top(text):
         tok = tok.strip()
         if not tok:
             continue
-        if not re.fullmatch(r"\d+", tok):
+        if re.fullmatch(r"\d+", tok):
+            modes.append(int(tok))
+            continue
+        if not env:
             raise ProgramSyntaxError("mode index %r is not an integer" % tok)
-        modes.append(int(tok))
+        val = _eval(tok, env)  # loop variables and integer arithmetic on them (``| [m, m + 1]``)
+        if isinstance(val, bool) or not isinstance(val, (int, np.integer)) or val < 0:
+            raise ProgramSyntaxError("mode index %r is not a non-negative integer" % tok)
+        modes.append(int(val))
     if not modes:
         raise ProgramSyntaxError("an operation needs at least one mode")
     return modes
@@ -272,7 +280,38 @@ def _loads_blackbird(text):
             if m.group(2):
                 _, opts = _parse_args(m.group(2), env, "=")
             prog.target = {"name": m.group(1), "options": opts}
-        elif head[0] in ("for", "type", "include"):
+        elif head[0] == "for":
+            # for <type> <var> in <start>:<stop>[:<step>]   or   in [v0, v1, ..]; the indented block is unrolled
+            m = re.match(r"^for\s+(int|float)\s+([A-Za-z_]\w*)\s+in\s+(.+)$", s)
+            if not m:
+                raise ProgramSyntaxError("bad for statement: %r" % s)
+            spec = m.group(3).strip()
+            if spec.startswith("["):
+                values = list(_eval(spec, env))
+            else:
+                parts = [_eval(x, env) for x in spec.split(":")]
+                if len(parts) not in (2, 3) or not all(isinstance(x, (int, np.integer)) for x in parts):
+                    raise ProgramSyntaxError("bad loop range %r (start:stop[:step], integers)" % spec)
+                values = list(range(int(parts[0]), int(parts[1]), int(parts[2]) if len(parts) == 3 else 1))
+            block = []
+            while i < len(lines) and (not strip(lines[i]).strip() or lines[i].startswith((" ", "\t"))):
+                if strip(lines[i]).strip():
+                    block.append(strip(lines[i]).strip())
+                i += 1
+            if not block:
+                raise ProgramSyntaxError("empty for block")
+            cast = int if m.group(1) == "int" else float
+            for v in values:
+                scope = dict(env)
+                scope[m.group(2)] = cast(v)
+                for stmt in block:
+                    mm = _OP_LINE.match(stmt)
+                    if not mm:
+                        raise ProgramSyntaxError("only operations are allowed inside a for block: %r" % stmt)
+                    args, kwargs = _parse_args(mm.group(2), scope, "=") if mm.group(2) and mm.group(2).strip() else ([], {})
+                    prog.operations.append({"op": mm.group(1), "args": args, "kwargs": kwargs,
+                                            "modes": _parse_modes(mm.group(3), scope)})
+        elif head[0] in ("type", "include"):
             raise NotImplementedError("Blackbird %r statements are not supported by the b200fock loader" % head[0])
         elif head[0] in _TYPES and len(head) > 1 and "=" in s and "|" not in s.split("=", 1)[0]:
             rest = head[1]

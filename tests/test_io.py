@@ -91,8 +91,35 @@ MeasureX | 0
     assert calls[-2] == ("measure_homodyne", 0.43, 2, {"select": 0.32}) and calls[-1] == ("measure_homodyne", 0.0, 0, {"select": None})
 
 
+def test_for_loops_are_unrolled():
+    prog = bio.loads("""name loops
+version 1.0
+float array phase[1, 4] =
+    0.1, 0.2, 0.3, 0.4
+for int m in 0:3
+    MZgate(phase[0, m], 0.5) | [m, m + 1]
+    Rgate(0.1 * m) | m
+
+for int k in [3, 1]
+    MeasureFock() | k
+for int j in 0:6:2
+    Sgate(0.1) | j
+""")
+    ops = prog.operations
+    assert [o["op"] for o in ops] == ["MZgate", "Rgate"] * 3 + ["MeasureFock"] * 2 + ["Sgate"] * 3
+    assert [o["modes"] for o in ops[:6]] == [[0, 1], [0], [1, 2], [1], [2, 3], [2]]
+    assert ops[2]["args"] == [0.2, 0.5] and ops[3]["args"] == [0.1]
+    assert [o["modes"] for o in ops[6:8]] == [[3], [1]] and [o["modes"] for o in ops[8:]] == [[0], [2], [4]]
+    with pytest.raises(bio.ProgramSyntaxError):
+        bio.loads("name x\nversion 1.0\nfor int m in 0:3\nSgate(0.1) | m\n")           # empty block
+    with pytest.raises(bio.ProgramSyntaxError):
+        bio.loads("name x\nversion 1.0\nfor int m in 0:3\n    float y = 2\n")           # not an operation
+    with pytest.raises(bio.ProgramSyntaxError):
+        bio.loads("name x\nversion 1.0\nfor int m in 0:2\n    Sgate(0.1) | m - 1\n")    # negative mode
+
+
 @pytest.mark.parametrize("bad,exc", [("Sgate(0.3 | 0", bio.ProgramSyntaxError), ("Sgate(foo) | 0", NameError),
-                                     ("for int m in 0:3\n    Sgate(0.1) | m", NotImplementedError),
+                                     ("type int x", NotImplementedError),
                                      ("Dgate(q0) | 1", NotImplementedError), ("Sgate({r}) | 0", NotImplementedError),
                                      ("Sgate(__import__('os')) | 0", bio.ProgramSyntaxError)])
 def test_bad_scripts_are_refused(bad, exc):
