@@ -4,7 +4,7 @@
 set -u
 mkdir -p gpurun_out
 TAG=${1:-q}
-SEL="inner_axis or diag_multi or apply_gate1_every_axis or apply_gate2_batched or gen_gate2"
+SEL="inner_axis or diag_multi or apply_gate1_every_axis or apply_gate2_batched or gen_gate2 or gram1 or outer_axis"
 for tool in memcheck racecheck synccheck; do
   timeout 900 compute-sanitizer --tool $tool --error-exitcode 7 --launch-timeout 120 \
       python -m pytest tests/test_gpu_kernels.py -q -m gpu -x -k "$SEL" > gpurun_out/r02${TAG}_sanitizer_${tool}.log 2>&1
