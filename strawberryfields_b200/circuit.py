@@ -235,6 +235,7 @@ class DeviceCircuit:
         snap.__dict__.update(self.__dict__)
         snap._pending = {}
         snap._opq = []
+        snap._defer_log = None
         snap._untouched = set()
         snap._inactive = set()
         snap._scratch = None
@@ -260,6 +261,8 @@ class DeviceCircuit:
         obj._norm_part = torch.zeros(4096, dtype=torch.float64, device=like.device)
         obj._shared = False
         obj._opq = []
+        obj._defer_log = None
+        obj._pregen = {}
         obj._set_identity_layout()
         return obj
 
@@ -622,6 +625,8 @@ class DeviceCircuit:
         log = self.__dict__.get("_defer_log")
         if log is None:
             return False
+        # host arrays are copied; ``DeviceParams`` tensors are kept by reference and read at the replay (a copy
+        # per gate would be a launch per gate): do not overwrite them before the state has been observed
         log.append((name, tuple(a.copy() if isinstance(a, np.ndarray) else a for a in args)))
         return True
 
