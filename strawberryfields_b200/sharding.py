@@ -1042,8 +1042,27 @@ class ShardedCircuit(DeviceCircuit):
         self._pending, self._opq, self._untouched, self._fresh = {}, [], set(), False
         dist.barrier(group=self._pg)
 
-    # ------------------------------------------------------------------ not sharded yet
+    # ------------------------------------------------------------------ modes (circuit.py:373-391)
+    def alloc(self, n=1):
+        """``add_mode``: tensor n vacuum modes onto the state (circuit.py:373-382).  The new axes are whole
+        (local) axes at the innermost positions, so every rank just copies its shard into the |0..0> slice of
+        a D^n (D^2n for density matrices) times larger one; no communication.  Collective."""
+        self._flush()
+        D = self._trunc
+        add = n if self._pure else 2 * n
+        old, old_size, old_axes = self._buf, self._size(), self._axes()
+        self._num_modes += n
+        self._phys = list(self._phys) + list(range(old_axes, old_axes + add))
+        self._set_layout(self._phys)
+        self._bufs = None
+        self._alloc()
+        L.call("b200_fill_zero", _ptr(self._buf), self._buf.numel(), self._stream())
+        self._gather(old, None, self._buf, [(old_size, 1, 0, D ** add)])
+        for m in range(self._num_modes - n, self._num_modes):
+            self._untouched.add(m)
+        self._fresh = False
+
     def _unsupported(self, *a, **k):
         raise NotImplementedError("this operation is not available on a sharded b200fock circuit yet")
 
-    alloc = dealloc = _unsupported
+    dealloc = _unsupported   # del_mode needs a partial trace of the sharded state

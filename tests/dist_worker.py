@@ -85,6 +85,22 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
         sys.exit(0 if ok else 1)
+    if "addmode" in flags:
+        # add_mode on a sharded state: the new mode is a whole (local) axis in the vacuum; gates on it work
+        W.run_calls(ob, calls + extra)
+        be.add_mode(1)
+        ob.add_mode(1)
+        be.beamsplitter(0.4, 0.3, 1, n)
+        ob.beamsplitter(0.4, 0.3, 1, n)
+        be.displacement(0.2, 0.1, n)
+        ob.displacement(0.2, 0.1, n)
+        st2, ost2 = be.state(), ob.state()
+        ok = bool(st2.num_modes == n + 1 and np.abs(st2.data - ost2.data).max() < 1e-12
+                  and abs(st2.trace() - ost2.trace()) < 1e-12)
+        print(json.dumps({"rank": dist.get_rank(), "world": dist.get_world_size(), "ok": ok}))
+        dist.barrier()
+        dist.destroy_process_group()
+        sys.exit(0 if ok else 1)
     if "ckpt" in flags:
         # per-rank checkpoint: save the shards, wipe the circuit, load them back -- same state
         import tempfile

@@ -101,6 +101,11 @@ def test_sharded_density_matrices_match_oracle_gloo(world, n, D, exchange, flag)
     _run("host", world, n, D, exchange, flags=[flag])
 
 
+def test_sharded_add_mode_gloo():
+    """add_mode on a sharded ket (circuit.py:373-382): no communication, the shard grows by a whole axis"""
+    _run("host", 2, 3, 4, "p2p", flags=["addmode"])
+
+
 def test_sharded_checkpoint_round_trip_gloo():
     """ShardedCircuit.save_shard / load_shard (on-disk checkpoint of a sharded ket)"""
     _run("host", 4, 5, 6, "p2p", flags=["ckpt"])
