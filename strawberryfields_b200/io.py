@@ -11,8 +11,11 @@ the parts of both languages a Fock-backend program uses:
   declarations (``float x = 0.3``, ``complex array U[4, 4] =`` + indented rows), comments, and operation
   lines ``Op(args, key=val) | modes``, and ``for <type> <var> in start:stop[:step]`` / ``in [..]`` loops over
   an indented block of operations (unrolled; the variable may appear in arguments, array subscripts and
-  mode lists).  Templates (``{par}``), ``type`` / ``include`` statements and measured parameters (``q0``) are
-  refused with ``NotImplementedError``.
+  mode lists).  Template parameters (``{par}``) and measured parameters (``q0`` = the last outcome of mode 0)
+  stay symbolic (:class:`Parameter`) until ``run(backend, args={..})`` binds / feeds them forward -- what
+  ``par_convert`` + ``par_evaluate`` do in the reference (``parameters.py:162-275``, ``engine.py:427-444``).
+  ``type`` / ``include`` statements (time-domain programs, out of scope) are refused with
+  ``NotImplementedError``.
 * XIR: ``options: .. end;`` and ``constants: .. end;`` blocks, ``use`` / declaration statements (ignored),
   and statements ``Op(args, key: val) | [wires];``.
 
@@ -55,14 +58,166 @@ class ProgramSyntaxError(ValueError):
     """A script that is not valid Blackbird / XIR (``blackbird.BlackbirdSyntaxError`` in the reference)."""
 
 
+class Parameter:
+    """A symbolic gate argument: a free parameter (Blackbird ``{name}``), a measured one (``q3`` = the latest
+    outcome of mode 3) or arithmetic on them.  The reference keeps these as sympy expressions over
+    ``FreeParameter`` / ``MeasuredParameter`` atoms (``parameters.py:318-420``); here it is a small expression
+    tree -- ``("free", name)``, ``("measured", mode)``, ``("bin", symbol, a, b)``, ``("neg", a)``,
+    ``("call", function, args)`` with numbers as leaves -- that :meth:`evaluate` walks once every atom has a
+    value, :meth:`substitute` partially binds and ``text`` writes back as Blackbird."""
+
+    __array_ufunc__ = None    # numpy scalars on the left hand side defer to __rmul__ & co.
+    _OPS = {"+": lambda x, y: x + y, "-": lambda x, y: x - y, "*": lambda x, y: x * y, "/": lambda x, y: x / y,
+            "**": lambda x, y: x ** y}
+
+    def __init__(self, node):
+        self.node = node
+
+    @classmethod
+    def free(cls, name):
+        return cls(("free", name))
+
+    @classmethod
+    def measured(cls, mode):
+        return cls(("measured", int(mode)))
+
+    @classmethod
+    def call(cls, name, args):
+        return cls(("call", name, tuple(a.node if isinstance(a, Parameter) else a for a in args)))
+
+    # ---- tree walks
+    @classmethod
+    def _atoms(cls, node, out):
+        if isinstance(node, tuple):
+            if node[0] in ("free", "measured"):
+                out.add(node)
+            else:
+                for child in (node[2] if node[0] == "call" else node[1:]):
+                    cls._atoms(child, out)
+        return out
+
+    @property
+    def atoms(self):
+        return self._atoms(self.node, set())
+
+    @property
+    def free_names(self):
+        return sorted(k for kind, k in self.atoms if kind == "free")
+
+    @property
+    def measured_modes(self):
+        return sorted(k for kind, k in self.atoms if kind == "measured")
+
+    @classmethod
+    def _value(cls, node, look, funcs):
+        if not isinstance(node, tuple):
+            return node
+        if node[0] in ("free", "measured"):
+            return look(*node)
+        if node[0] == "bin":
+            return cls._OPS[node[1]](cls._value(node[2], look, funcs), cls._value(node[3], look, funcs))
+        if node[0] == "neg":
+            return -cls._value(node[1], look, funcs)
+        return funcs[node[1]](*[cls._value(a, look, funcs) for a in node[2]])
+
+    def evaluate(self, lookup, funcs=None):
+        """``lookup(kind, key)`` supplies the atoms (numbers, or sympy symbols for ``to_sf``)."""
+        return self._value(self.node, lookup, _FUNCS if funcs is None else funcs)
+
+    @classmethod
+    def _subst(cls, node, values):
+        if not isinstance(node, tuple):
+            return node
+        if node[0] == "free":
+            return values.get(node[1], node)
+        if node[0] == "measured":
+            return node
+        if node[0] == "call":
+            args = tuple(cls._subst(a, values) for a in node[2])
+            return node[:2] + (args,) if any(isinstance(a, tuple) for a in args) else _FUNCS[node[1]](*args)
+        kids = [cls._subst(c, values) for c in (node[2:] if node[0] == "bin" else node[1:])]
+        if any(isinstance(c, tuple) for c in kids):
+            return (node[:2] if node[0] == "bin" else node[:1]) + tuple(kids)
+        return cls._OPS[node[1]](*kids) if node[0] == "bin" else -kids[0]
+
+    def substitute(self, values):
+        """bind some free parameters; a number if nothing symbolic is left, else a new :class:`Parameter`"""
+        node = self._subst(self.node, values)
+        return Parameter(node) if isinstance(node, tuple) else node
+
+    @classmethod
+    def _text(cls, node, top=True):
+        if not isinstance(node, tuple):
+            t = _fmt(node)
+            return "(%s)" % t if not top and (t.startswith("-") or isinstance(node, (complex, np.complexfloating))) else t
+        if node[0] == "free":
+            return "{%s}" % node[1]
+        if node[0] == "measured":
+            return "q%d" % node[1]
+        if node[0] == "call":
+            return "%s(%s)" % (node[1], ", ".join(cls._text(a) for a in node[2]))
+        t = "-%s" % cls._text(node[1], False) if node[0] == "neg" else \
+            "%s %s %s" % (cls._text(node[2], False), node[1], cls._text(node[3], False))
+        return t if top else "(%s)" % t
+
+    @property
+    def text(self):
+        return self._text(self.node)
+
+    # ---- arithmetic
+    def _bin(self, sym, other, swap=False):
+        o = other.node if isinstance(other, Parameter) else other
+        return Parameter(("bin", sym, o, self.node) if swap else ("bin", sym, self.node, o))
+
+    def __add__(self, o): return self._bin("+", o)
+    def __radd__(self, o): return self._bin("+", o, True)
+    def __sub__(self, o): return self._bin("-", o)
+    def __rsub__(self, o): return self._bin("-", o, True)
+    def __mul__(self, o): return self._bin("*", o)
+    def __rmul__(self, o): return self._bin("*", o, True)
+    def __truediv__(self, o): return self._bin("/", o)
+    def __rtruediv__(self, o): return self._bin("/", o, True)
+    def __pow__(self, o): return self._bin("**", o)
+    def __rpow__(self, o): return self._bin("**", o, True)
+    def __neg__(self): return Parameter(("neg", self.node))
+    def __pos__(self): return self
+
+    def __repr__(self):
+        return "Parameter(%s)" % self.text
+
+
+_FREE_PREFIX = "_b200_free_"   # ``{name}`` is rewritten to this prefix + name so that ``ast`` can parse the expression
+
+
+def _symbolic(v):
+    if isinstance(v, Parameter):
+        return True
+    if isinstance(v, (list, tuple)):
+        return any(_symbolic(x) for x in v)
+    return isinstance(v, np.ndarray) and v.dtype == object and any(_symbolic(x) for x in v.flat)
+
+
+def _resolve(v, lookup, funcs=None):
+    if isinstance(v, Parameter):
+        return v.evaluate(lookup, funcs)
+    if isinstance(v, (list, tuple)):
+        return type(v)(_resolve(x, lookup, funcs) for x in v)
+    if isinstance(v, np.ndarray) and v.dtype == object:
+        out = np.array([_resolve(x, lookup, funcs) for x in v.flat], dtype=object).reshape(v.shape)
+        try:
+            return out.astype(complex) if any(isinstance(x, complex) for x in out.flat) else out.astype(float)
+        except (TypeError, ValueError):
+            return out
+    return v
+
+
 def _eval(expr, env):
     """Evaluate a Blackbird / XIR parameter expression: numbers (``1+2j`` included), declared variables,
     ``pi``, arithmetic and the usual real functions.  Anything else is refused (no ``eval``)."""
     expr = expr.strip()
     if not expr:
         raise ProgramSyntaxError("empty expression")
-    if re.fullmatch(r"q\d+", expr):
-        raise NotImplementedError("measured parameters (%s) are not supported by the b200fock loader" % expr)
+    expr = re.sub(r"\{\s*([A-Za-z_]\w*)\s*\}", lambda m: _FREE_PREFIX + m.group(1), expr)
     try:
         tree = ast.parse(expr, mode="eval")
     except SyntaxError as exc:
@@ -79,8 +234,10 @@ def _eval(expr, env):
                 return env[node.id]
             if node.id in _CONSTS:
                 return _CONSTS[node.id]
+            if node.id.startswith(_FREE_PREFIX):
+                return Parameter.free(node.id[len(_FREE_PREFIX):])
             if re.fullmatch(r"q\d+", node.id):
-                raise NotImplementedError("measured parameters (%s) are not supported by the b200fock loader" % node.id)
+                return Parameter.measured(int(node.id[1:]))
             raise NameError("name %r is not defined in the script" % node.id)
         elif isinstance(node, ast.UnaryOp) and isinstance(node.op, (ast.USub, ast.UAdd)):
             v = ev(node.operand)
@@ -99,7 +256,10 @@ def _eval(expr, env):
                 return a ** b
         elif isinstance(node, ast.Call) and isinstance(node.func, ast.Name) and node.func.id in _FUNCS \
                 and not node.keywords:
-            return _FUNCS[node.func.id](*[ev(a) for a in node.args])
+            vals = [ev(a) for a in node.args]
+            if any(isinstance(v, Parameter) for v in vals):
+                return Parameter.call(node.func.id, vals)
+            return _FUNCS[node.func.id](*vals)
         elif isinstance(node, (ast.List, ast.Tuple)):
             return [ev(e) for e in node.elts]
         elif isinstance(node, ast.Subscript) and isinstance(node.value, ast.Name) and node.value.id in env:
@@ -191,32 +351,111 @@ class CircuitProgram:
 
     @property
     def backend_options(self):
-        return {k: self.options[k] for k in ("cutoff_dim",) if k in self.options}
+        opts = dict(self.target.get("options", {}))   # blackbird_io.py:84-85 / xir_io.py:130-131
+        return {k: opts[k] for k in ("cutoff_dim",) if k in opts} | {k: self.options[k] for k in ("cutoff_dim",) if k in self.options}
+
+    # ------------------------------------------------------------------ symbolic parameters
+    def _symbols(self):
+        for op in self.operations:
+            for v in list(op.get("args", [])) + list(op.get("kwargs", {}).values()):
+                stack = [v]
+                while stack:
+                    x = stack.pop()
+                    if isinstance(x, Parameter):
+                        yield x
+                    elif isinstance(x, (list, tuple)):
+                        stack.extend(x)
+                    elif isinstance(x, np.ndarray) and x.dtype == object:
+                        stack.extend(x.flat)
+
+    @property
+    def free_parameters(self):
+        """names of the template parameters (``{name}``) of the script, sorted"""
+        return sorted({n for p in self._symbols() for n in p.free_names})
+
+    @property
+    def is_template(self):
+        return bool(self.free_parameters)
+
+    @property
+    def has_feed_forward(self):
+        return any(p.measured_modes for p in self._symbols())
+
+    @staticmethod
+    def _lookup(args, samples):
+        def look(kind, key):
+            if kind == "free":
+                if args is None or key not in args:
+                    raise ValueError("free parameter {%s} of the program has no value: pass args={%r: ..}" % (key, key))
+                return args[key]
+            if key not in samples:
+                # the reference raises ParameterError from MeasuredParameter._eval_evalf (parameters.py:352-362)
+                raise ValueError("parameter q%d is used before mode %d has been measured" % (key, key))
+            return samples[key][-1]
+        return look
+
+    def bind(self, **values):
+        """A copy with the given free parameters replaced by numbers (measured parameters stay symbolic)."""
+        unknown = sorted(set(values) - set(self.free_parameters))
+        if unknown:
+            raise ValueError("the program has no free parameter(s) %s" % ", ".join(unknown))
+
+        def sub(v):
+            if isinstance(v, Parameter):
+                return v.substitute(values)
+            if isinstance(v, (list, tuple)):
+                return type(v)(sub(x) for x in v)
+            if isinstance(v, np.ndarray) and v.dtype == object:
+                return _resolve(np.array([sub(x) for x in v.flat], dtype=object).reshape(v.shape), None)
+            return v
+
+        ops = [{"op": op["op"], "args": [sub(a) for a in op.get("args", [])],
+                "kwargs": {k: sub(a) for k, a in op.get("kwargs", {}).items()}, "modes": list(op["modes"])}
+               for op in self.operations]
+        return CircuitProgram(self.name, self.version, self.target, ops, self.options)
 
     # ------------------------------------------------------------------ lowering to backend calls
-    def calls(self):
-        """``[(method, *args)]``: the ``BaseFock`` calls of the program (measurements included, in place)."""
+    def _lower_op(self, op, look):
+        args = [_resolve(a, look) for a in op.get("args", [])]
+        kwargs = {k: _resolve(a, look) for k, a in op.get("kwargs", {}).items()}
+        return lower(op["op"], args, kwargs, op["modes"])
+
+    def calls(self, args=None):
+        """``[(method, *args)]``: the ``BaseFock`` calls of the program (measurements included, in place).
+        ``args`` binds template parameters; a program with measured parameters has no static call list
+        (``run`` feeds the outcomes forward)."""
+        if self.has_feed_forward:
+            raise ValueError("the program uses measured parameters (q<mode>): its calls depend on the outcomes, use run()")
+        look = self._lookup(args, {})
         out = []
         for op in self.operations:
-            out.extend(lower(op["op"], op.get("args", []), op.get("kwargs", {}), op["modes"]))
+            out.extend(self._lower_op(op, look))
         return out
 
-    def run(self, backend, cutoff_dim=None, **begin_options):
-        """``begin_circuit`` + every call; returns ``{mode: [outcomes]}`` like ``Result.samples_dict``."""
+    def run(self, backend, cutoff_dim=None, args=None, **begin_options):
+        """``begin_circuit`` + every call; returns ``{mode: [outcomes]}`` like ``Result.samples_dict``.
+        ``args = {name: value}`` binds the template parameters (``engine.run(prog, args=..)``,
+        ``engine.py:304-306``); a measured parameter ``q<m>`` takes the latest outcome of mode m when the
+        operation that uses it is reached (``engine.py:427-444`` + ``parameters.py:352-362``)."""
         D = cutoff_dim if cutoff_dim is not None else self.backend_options.get("cutoff_dim")
         if D is None:
             raise ValueError("Argument 'cutoff_dim' must be passed to the Fock backend")
+        missing = sorted(set(self.free_parameters) - set(args or {}))
+        if missing:
+            raise ValueError("free parameter(s) %s of the program have no value: pass args={..}" % ", ".join(missing))
         backend.begin_circuit(self.num_subsystems, cutoff_dim=int(D), **begin_options)
         samples = {}
-        for call in self.calls():
-            ret = getattr(backend, call[0])(*call[1:-1], **call[-1]) if isinstance(call[-1], dict) else \
-                getattr(backend, call[0])(*call[1:])
-            if call[0].startswith("measure_"):
-                modes = call[2] if call[0] == "measure_homodyne" else call[1]
-                modes = [modes] if isinstance(modes, int) else list(modes)
-                vals = np.asarray(ret).reshape(-1)
-                for m, v in zip(modes, vals):
-                    samples.setdefault(m, []).append(v.item() if hasattr(v, "item") else v)
+        look = self._lookup(args, samples)
+        for op in self.operations:
+            for call in self._lower_op(op, look):
+                ret = getattr(backend, call[0])(*call[1:-1], **call[-1]) if isinstance(call[-1], dict) else \
+                    getattr(backend, call[0])(*call[1:])
+                if call[0].startswith("measure_"):
+                    modes = call[2] if call[0] == "measure_homodyne" else call[1]
+                    modes = [modes] if isinstance(modes, int) else list(modes)
+                    vals = np.asarray(ret).reshape(-1)
+                    for m, v in zip(modes, vals):
+                        samples.setdefault(m, []).append(v.item() if hasattr(v, "item") else v)
         return samples
 
     def to_sf(self):
@@ -225,14 +464,19 @@ class CircuitProgram:
         from strawberryfields import ops
 
         prog = sf.Program(self.num_subsystems, name=self.name)
+        funcs = {k: getattr(sf.math, k) for k in _FUNCS if hasattr(sf.math, k)}
         with prog.context as q:
+            def look(kind, key):   # the reference's atoms (par_convert, parameters.py:249-275)
+                return prog.params(key) if kind == "free" else q[key].par
+
             for op in self.operations:
                 if op["op"] not in ops.__all__:
                     raise NameError("Quantum operation {} not defined!".format(op["op"]))
                 gate = getattr(ops, op["op"])
                 regs = [q[i] for i in op["modes"]]
                 if op.get("args") or op.get("kwargs"):
-                    gate(*op.get("args", []), **op.get("kwargs", {})) | regs  # noqa: pylint: disable=expression-not-assigned
+                    gate(*[_resolve(a, look, funcs) for a in op.get("args", [])],
+                         **{k: _resolve(a, look, funcs) for k, a in op.get("kwargs", {}).items()}) | regs  # noqa
                 else:
                     (gate() if isinstance(gate, type) else gate) | regs  # noqa
         prog.run_options.update(self.run_options)
@@ -249,8 +493,6 @@ _TYPES = ("int", "float", "complex", "str", "bool")
 
 
 def _loads_blackbird(text):
-    if re.search(r"\{\s*[A-Za-z_]\w*\s*\}", text):
-        raise NotImplementedError("Blackbird templates ({parameter}) are not supported by the b200fock loader")
     prog = CircuitProgram()
     env = {}
     lines = text.splitlines()
@@ -326,7 +568,8 @@ def _loads_blackbird(text):
                     rows.append(strip(lines[i]).strip())
                     i += 1
                 data = [[_eval(x, env) for x in _split_top(r) if x.strip()] for r in rows]
-                arr = np.array(data, dtype={"int": int, "float": float, "complex": complex}.get(head[0], object))
+                arr = np.array(data, dtype=object if _symbolic(data) else
+                               {"int": int, "float": float, "complex": complex}.get(head[0], object))
                 if m.group(2):
                     shape = [int(_eval(x, env)) for x in m.group(2).split(",") if x.strip()]
                     if list(arr.shape) != shape and arr.size == int(np.prod(shape)):
@@ -350,6 +593,8 @@ def _loads_blackbird(text):
 
 
 def _fmt(v):
+    if isinstance(v, Parameter):
+        return v.text
     if isinstance(v, np.ndarray):
         return "[" + ", ".join(_fmt(x) for x in v) + "]"
     if isinstance(v, (list, tuple)):
@@ -430,6 +675,8 @@ def _loads_xir(text):
 
 
 def _dumps_xir(prog):
+    if any(True for _ in prog._symbols()):
+        raise NotImplementedError("free / measured parameters are written as Blackbird only")
     out = []
     opts = dict(prog.options)
     if prog.name:

@@ -120,7 +120,7 @@ for int j in 0:6:2
 
 @pytest.mark.parametrize("bad,exc", [("Sgate(0.3 | 0", bio.ProgramSyntaxError), ("Sgate(foo) | 0", NameError),
                                      ("type int x", NotImplementedError),
-                                     ("Dgate(q0) | 1", NotImplementedError), ("Sgate({r}) | 0", NotImplementedError),
+                                     ("include \"lib.xbb\"", NotImplementedError),
                                      ("Sgate(__import__('os')) | 0", bio.ProgramSyntaxError)])
 def test_bad_scripts_are_refused(bad, exc):
     with pytest.raises(exc):
@@ -301,3 +301,141 @@ def test_lowering_equals_the_reference_front_end():
         getattr(ob, c[0])(*c[1:])
     got = ob.state()
     assert np.abs(got.data - want.data).max() < 1e-12
+
+
+# ------------------------------------------------------------------ templates and measured parameters
+TEMPLATE = """name tmpl
+version 1.0
+target fock (cutoff_dim=5)
+float a = 0.3
+Sgate({r}, 0.1) | 0
+Dgate(a*{alpha}**2 + 0.1, phi=sqrt({r})) | 1
+BSgate({theta}, pi/2 - {theta}) | [0, 1]
+"""
+
+
+def test_template_parameters_stay_symbolic_until_bound():
+    prog = bio.loads(TEMPLATE)
+    assert prog.is_template and prog.free_parameters == ["alpha", "r", "theta"] and not prog.has_feed_forward
+    assert isinstance(prog.operations[0]["args"][0], bio.Parameter) and prog.operations[0]["args"][1] == 0.1
+    # written back as Blackbird and loaded again: the same script
+    assert bio.loads(prog.serialize()).serialize() == prog.serialize()
+    assert "{alpha}" in prog.serialize() and "sqrt({r})" in prog.serialize()
+    with pytest.raises(NotImplementedError):
+        prog.serialize("xir")
+    with pytest.raises(ValueError, match="alpha"):
+        prog.calls(args={"r": 0.2, "theta": 0.1})
+    vals = {"r": 0.25, "alpha": 0.5, "theta": 0.4}
+    calls = prog.calls(args=vals)
+    assert calls[0] == ("squeeze", 0.25, 0.1, 0)
+    assert calls[1][0] == "displacement" and abs(calls[1][1] - (0.3 * 0.25 + 0.1)) < 1e-15 and calls[1][2] == 0.5
+    assert calls[2] == ("beamsplitter", 0.4, np.pi / 2 - 0.4, 0, 1)
+    # partial binding keeps the rest symbolic and rewrites the text
+    part = prog.bind(r=0.25)
+    assert part.free_parameters == ["alpha", "theta"] and part.operations[0]["args"][0] == 0.25
+    assert part.operations[1]["kwargs"]["phi"] == 0.5 and "{r}" not in part.serialize()
+    assert part.bind(alpha=0.5, theta=0.4).calls() == calls
+    with pytest.raises(ValueError, match="no free parameter"):
+        prog.bind(gamma=1.0)
+
+
+def test_parameter_arithmetic_with_numpy_scalars():
+    x = bio.Parameter.free("x")
+    e = np.float64(2.0) * x - (1 + 2j) / x ** 2 + (-x)
+    assert e.free_names == ["x"] and e.measured_modes == []
+    assert abs(e.evaluate(lambda kind, key: 0.5) - (1.0 - (1 + 2j) / 0.25 - 0.5)) < 1e-15
+    assert e.substitute({"x": 0.5}) == e.evaluate(lambda kind, key: 0.5)
+    m = bio.Parameter.measured(3) * x
+    assert m.measured_modes == [3] and m.substitute({"x": 2}).text == "q3 * 2"
+    assert bio.loads("Rgate(%s) | 0" % e.text).operations[0]["args"][0].evaluate(lambda k, n: 0.5) == e.evaluate(lambda k, n: 0.5)
+
+
+def test_template_runs_with_args(host):
+    from oracle.fock_oracle import OracleBackend
+    from strawberryfields_b200.backend import B200FockBackend
+
+    prog = bio.loads(TEMPLATE)
+    vals = {"r": 0.25, "alpha": 0.5, "theta": 0.4}
+    be = B200FockBackend()
+    with pytest.raises(ValueError, match="alpha, r, theta"):
+        prog.run(be)
+    prog.run(be, args=vals)          # cutoff from the target line
+    ob = OracleBackend()
+    ob.begin_circuit(2, cutoff_dim=5)
+    ob.squeeze(0.25, 0.1, 0)
+    ob.displacement(0.3 * 0.25 + 0.1, 0.5, 1)
+    ob.beamsplitter(0.4, np.pi / 2 - 0.4, 0, 1)
+    assert np.abs(be.state().ket() - ob.state().ket()).max() < 1e-12
+
+
+FEED_FORWARD = """name ff
+version 1.0
+Fock(2) | 0
+Squeezed(0.6, 0.0) | 1
+BSgate(0.7, 0.3) | [0, 1]
+MeasureFock() | 0
+Rgate(q0*pi/3) | 1
+Dgate(0.1*q0 + 0.05, 0.0) | 2
+MeasureFock() | 1
+Rgate(q0 - q1) | 2
+"""
+
+
+@pytest.mark.parametrize("seed", [3, 11, 12])
+def test_measured_parameters_are_fed_forward(host, seed):
+    """``q<m>`` takes the latest outcome of mode m when its operation is reached (engine.py:427-444)."""
+    from oracle.fock_oracle import OracleBackend
+    from strawberryfields_b200.backend import B200FockBackend
+
+    prog = bio.loads(FEED_FORWARD)
+    assert prog.has_feed_forward and not prog.is_template
+    with pytest.raises(ValueError, match="measured parameters"):
+        prog.calls()
+    be = B200FockBackend()
+    np.random.seed(seed)
+    samples = prog.run(be, cutoff_dim=6)
+    ob = OracleBackend()
+    ob.begin_circuit(3, cutoff_dim=6)
+    np.random.seed(seed)
+    ob.prepare_fock_state(2, 0)
+    ob.prepare_squeezed_state(0.6, 0.0, 1)
+    ob.beamsplitter(0.7, 0.3, 0, 1)
+    n0 = int(np.asarray(ob.measure_fock([0])).reshape(-1)[0])
+    ob.rotation(n0 * np.pi / 3, 1)
+    ob.displacement(0.1 * n0 + 0.05, 0.0, 2)
+    n1 = int(np.asarray(ob.measure_fock([1])).reshape(-1)[0])
+    ob.rotation(n0 - n1, 2)
+    assert samples == {0: [n0], 1: [n1]}
+    assert np.abs(be.state().dm() - ob.state().dm()).max() < 1e-12
+
+
+def test_measured_parameter_before_its_measurement(host):
+    from strawberryfields_b200.backend import B200FockBackend
+
+    with pytest.raises(ValueError, match="before mode 1 has been measured"):
+        bio.loads("Rgate(q1) | 0\nMeasureFock() | 1").run(B200FockBackend(), cutoff_dim=3)
+
+
+@pytest.mark.reference
+def test_symbolic_programs_run_like_the_reference_engine(host):
+    """``to_sf`` hands the reference FreeParameter / MeasuredParameter atoms (par_convert, parameters.py:249-275);
+    its engine binds ``args`` and feeds outcomes forward -- the result must equal ``CircuitProgram.run``."""
+    from oracle import ref_shim
+    from strawberryfields_b200.backend import B200FockBackend
+
+    sf = ref_shim.install()
+    script = TEMPLATE + "MeasureFock() | 0\nRgate(q0*{theta} + sin(q0)) | 1\n"
+    prog = bio.loads(script)
+    vals = {"r": 0.6, "alpha": 0.5, "theta": 0.4}
+    sfp = prog.to_sf()
+    assert sorted(sfp.free_params) == prog.free_parameters
+    eng = sf.Engine("fock", backend_options={"cutoff_dim": 5})
+    for seed in (1, 5, 6):
+        np.random.seed(seed)
+        res = eng.run(sfp, args=vals)
+        be = B200FockBackend()
+        np.random.seed(seed)
+        samples = prog.run(be, args=vals)
+        assert samples[0] == [int(np.asarray(res.samples).reshape(-1)[0])]
+        assert np.abs(be.state().dm() - res.state.dm()).max() < 1e-12
+        eng.reset()
