@@ -209,10 +209,10 @@ class B200FockBackend(_Base):
         self.circuit.prepare_mode_fock(n, self._remap_modes(mode))
 
     def prepare_ket_state(self, state, modes):
-        self.circuit.prepare_multimode(state, self._remap_modes(modes))
+        self.circuit.prepare_multimode(state, self._remap_modes(modes), input_state_is_pure=True)
 
     def prepare_dm_state(self, state, modes):
-        self.circuit.prepare_multimode(state, self._remap_modes(modes))
+        self.circuit.prepare_multimode(state, self._remap_modes(modes), input_state_is_pure=False)
 
     def prepare_gkp(self, state, epsilon, ampl_cutoff, representation="real", shape="square", mode=None):
         """Finite-energy GKP qubit state ``[theta, phi]`` (backend.py:297-329)."""

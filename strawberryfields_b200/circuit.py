@@ -1086,12 +1086,16 @@ class DeviceCircuit:
         return out
 
     # ------------------------------------------------------------------ preparation (circuit.py:393-535)
-    def prepare_multimode(self, state, modes):
+    def prepare_multimode(self, state, modes, input_state_is_pure=None):
+        """``input_state_is_pure`` only matters on a batched circuit, where a ``[B, D^k]`` array of kets and a
+        ``[D^k, D^k]`` density matrix can have the same shape (``tfbackend/circuit.py:343-396``)."""
         if isinstance(modes, int):
             modes = [modes]
         modes = list(modes)
         if self._batched:
-            self._prepare_batched(state, modes)
+            if self._prepare_batched(state, modes, input_state_is_pure):
+                return
+            self._prepare_batched_general(state, modes, input_state_is_pure)
             return
         self._replay()
         D, n, k = self._trunc, self._num_modes, len(modes)
@@ -1187,37 +1191,133 @@ class DeviceCircuit:
         self._scratch = None
         self._touch(*modes)
 
-    def _prepare_batched(self, state, modes):
+    def _prepare_batched(self, state, modes, input_state_is_pure=None):
         """Batched circuits (TF-backend semantics, ``tfbackend/circuit.py:343-396``: one state for every batch
-        entry, or an array with a leading batch axis): single-mode KETS on modes that are still the untouched
-        vacuum -- the input encodings of a batched program.  |v> = (|v><0|) |0>, so the preparation is queued
-        as a rank-one single-mode operator (per entry when the kets differ) and costs what a gate costs.
-        Anything else would need a partial trace of every batch entry: not supported."""
+        entry, or an array with a leading batch axis).  Fast path: single-mode KETS on modes that are still the
+        untouched vacuum -- the input encodings of a batched program.  |v> = (|v><0|) |0>, so the preparation is
+        queued as a rank-one single-mode operator (per entry when the kets differ) and costs what a gate costs.
+        Returns False when the call is not of that kind (``_prepare_batched_general`` takes it)."""
         D, B = self._trunc, self._B
         st = np.asarray(state, dtype=C128)
-        if len(modes) != 1 or st.shape not in ((D,), (B, D)):
-            raise NotImplementedError("batched b200fock circuits prepare single-mode kets only")
+        if len(modes) != 1 or st.shape not in ((D,), (B, D)) or (st.ndim == 2 and B == D and input_state_is_pure is False):
+            return False    # (the last case: a D x D density matrix on a circuit whose batch size equals the cutoff)
         m = modes[0]
         log = self.__dict__.get("_defer_log")
         if log and any(name != "_queue_dense" or args[1] == m for name, args in log):
             self._replay()  # gates were recorded before this preparation: apply them first
         if m not in self._untouched or m in self._pending:
-            raise NotImplementedError("batched b200fock circuits prepare states on untouched modes only")
+            return False
         kets = st.reshape(-1, D)
         tab = np.zeros((kets.shape[0], D, D), dtype=C128)
         tab[:, :, 0] = kets
         table = TABLES.get(self._key("ketprep", tab.tobytes()),
                            lambda: torch.from_numpy(tab).to(self.device))
         if self._defer("_queue_dense", table, m):
-            return
+            return True
         self._queue_dense(table, m)
+        return True
+
+    def _prepare_batched_general(self, state, modes, input_state_is_pure=None):
+        """Everything else on a batched circuit (``tfbackend/circuit.py:343-396`` + ``_replace_and_update``):
+        kets or density matrices on any modes, one for all entries or one per entry; the three cases of the
+        unbatched method with the batch as one more (outermost) gather axis."""
+        self._replay()
+        self._flush()
+        self._canonicalize()
+        D, n, k, B = self._trunc, self._num_modes, len(modes), self._B
+        if len(modes) != len(set(modes)):
+            raise ValueError("The specified modes cannot appear multiple times.")
+        st = np.asarray(state)
+        shapes = {"ket": [(D,) * k, (D ** k,)], "dm": [(D,) * (2 * k), (D ** k, D ** k)]}
+        kind = per_entry = None
+        # (kind, one per batch entry?) in the order the flag resolves equal shapes (B = D^k)
+        if input_state_is_pure:
+            cands = [("ket", True), ("ket", False), ("dm", False), ("dm", True)]
+        elif input_state_is_pure is None:
+            cands = [("ket", False), ("dm", False), ("ket", True), ("dm", True)]
+        else:
+            cands = [("dm", False), ("dm", True), ("ket", False), ("ket", True)]
+        for kd, pe in cands:
+            if any(st.shape == ((B,) + sh if pe else sh) for sh in shapes[kd]):
+                kind, per_entry = kd, pe
+                break
+        if kind is None:
+            raise ValueError("Incorrect shape for state preparation")
+        is_ket = kind == "ket"
+        inner = (D,) * (k if is_ket else 2 * k)
+        host = np.ascontiguousarray(st.astype(C128)).reshape(((B,) if per_entry else ()) + inner)
+        sb = (lambda per: per) if per_entry else (lambda per: 0)    # stride of the batch axis in the new state
+        per = self._size()
+
+        def finish(out, pure, touched=True):
+            self._buf, self._shared, self._scratch = out, False, None
+            if touched:
+                self._touch(*modes)
+
+        if n == k:      # the whole register is replaced (circuit.py:441-444)
+            self._pure = bool(is_ket)
+            self._set_identity_layout()
+            naxes = self._axes()
+            new_per = D ** naxes
+            src = torch.from_numpy(np.ascontiguousarray(host).reshape(-1)).to(self.device)
+            out = self._new(B * new_per)
+            oa = [(B, sb(new_per), 0, new_per)]
+            for f in range(n):
+                j = modes.index(f)
+                for t, ax in enumerate(self._mode_axes(f)):
+                    src_axis = j if self._pure else 2 * j + t
+                    oa.append((D, D ** (naxes - 1 - src_axis), 0, self._stride(ax)))
+            self._gather(src, None, out, oa)
+            finish(out, is_ket, touched=False)
+            self._untouched = set()
+            return
+
+        if self._pure and is_ket and not self._strict and all(m in self._untouched for m in modes):
+            # still the product vacuum on these modes: the state stays pure (SURVEY F7)
+            src = torch.from_numpy(host.reshape(-1)).to(self.device)
+            out = self._new(self._buf.numel())
+            oa = [(B, per, sb(D ** k), per)]
+            for f in range(n):
+                if f in modes:
+                    oa.append((D, 0, D ** (k - 1 - modes.index(f)), self._stride(f)))
+                else:
+                    oa.append((D, self._stride(f), 0, self._stride(f)))
+            self._gather(self._buf, src, out, oa)
+            finish(out, True)
+            return
+
+        # general case: rho_b <- Tr_modes(rho_b) (x) new_b
+        self._to_mixed()
+        if is_ket:
+            mix = [x for i in range(k) for x in (i, k + i)]
+            if per_entry:
+                host = np.stack([np.multiply.outer(h, h.conj()).transpose(mix) for h in host])
+            else:
+                host = np.multiply.outer(host, host.conj()).transpose(mix)
+        src = torch.from_numpy(np.ascontiguousarray(host).reshape(-1)).to(self.device)
+        keep = [m for m in range(n) if m not in modes]
+        red = self._partial_trace_keep(keep)
+        kk = len(keep)
+        out = self._new(B * D ** (2 * n))
+        oa = [(B, D ** (2 * kk), sb(D ** (2 * k)), D ** (2 * n))]
+        for f in range(n):
+            for t in (0, 1):
+                sc = D ** (2 * n - 1 - (2 * f + t))
+                if f in modes:
+                    j = modes.index(f)
+                    oa.append((D, 0, D ** (2 * k - 1 - (2 * j + t)), sc))
+                else:
+                    j = keep.index(f)
+                    oa.append((D, D ** (2 * kk - 1 - (2 * j + t)), 0, sc))
+        self._gather(red, src, out, oa)
+        finish(out, False)
 
     def prepare(self, state, mode):
         self.prepare_multimode(state, [mode] if isinstance(mode, int) else mode)
 
     def _prepare_ket(self, ket, mode):
         if self._batched:
-            self._prepare_batched(ket, [mode])
+            self.prepare_multimode(ket, [mode], input_state_is_pure=True)
         elif self._pure or (mode in self._inactive and self._num_modes > 1):  # lazy vacuum: the factor is the ket
             self.prepare(ket, mode)
         else:

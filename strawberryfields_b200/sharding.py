@@ -977,7 +977,7 @@ class ShardedCircuit(DeviceCircuit):
         dist.all_reduce(ri, group=self._pg)
         return out.view(1, -1)
 
-    def prepare_multimode(self, state, modes):
+    def prepare_multimode(self, state, modes, input_state_is_pure=None):
         """Single-mode kets on modes that are still the untouched vacuum (the inputs of a boson-sampling
         program): |v> = (|v><0|) |0>, so the preparation is queued as a rank-one single-mode operator and
         costs what a gate costs.  Anything else needs a partial trace of the sharded state: not yet."""

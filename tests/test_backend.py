@@ -330,7 +330,79 @@ def test_batched_preparations_and_measure_fock(host_backend, lazy):
         assert np.abs(post[b] - ob.state().data).max() < TOL
     with pytest.raises(ValueError, match="shape of 'select'"):
         be.measure_fock([0, 2], select=[1, 0, 0])
-    with pytest.raises(NotImplementedError):
-        be.prepare_fock_state(1, 0)                   # mode 0 is no longer the untouched vacuum
-    with pytest.raises(NotImplementedError):
-        be.prepare_ket_state(np.ones((D, D)) / D, [1, 2])
+
+
+def batched_general_preparations(make_backend):
+    """Preparations a batched circuit cannot queue as a rank-one operator (TF-backend ``prepare_multimode`` +
+    ``_replace_and_update``, tfbackend/circuit.py:343-396): multi-mode kets, density matrices, modes that have
+    been touched, one state for all entries or one per entry -- every batch entry against the oracle run
+    alone.  (Shared with tests/test_vacuum_lazy.py, which holds the GPU variant: last file of the suite.)"""
+    from oracle.fock_oracle import OracleBackend
+
+    D, B, n = 4, 3, 3
+    rs = np.random.RandomState(21)
+
+    th = rs.uniform(0.2, 1.0, B)
+    k2 = rs.randn(B, D, D) + 1j * rs.randn(B, D, D)
+    k2 /= np.sqrt((np.abs(k2) ** 2).sum(axis=(1, 2), keepdims=True))          # per-entry two-mode kets
+    k1 = rs.randn(D) + 1j * rs.randn(D)
+    k1 /= np.linalg.norm(k1)                                                  # one single-mode ket for all
+    a = rs.randn(B, D, D) + 1j * rs.randn(B, D, D)
+    dm = np.einsum("bij,bkj->bik", a, a.conj())
+    dm /= np.trace(dm, axis1=1, axis2=2)[:, None, None]                       # per-entry single-mode density matrices
+    full = rs.randn(D, D, D) + 1j * rs.randn(D, D, D)
+    full /= np.sqrt((np.abs(full) ** 2).sum())                                # whole register, one for all
+
+    def steps(b_, e):
+        """e = batch entry for the oracle (None: the batched backend gets the whole arrays)"""
+        pick = (lambda x: x) if e is None else (lambda x: x[e])
+        b_.prepare_ket_state(pick(k2), [2, 0])                 # untouched modes, unordered: stays pure
+        b_.beamsplitter(pick(th) if e is None else float(th[e]), 0.3, 0, 1)
+        yield "pure two-mode kets"
+        b_.prepare_ket_state(k1, [1])                          # touched mode: the state becomes mixed
+        b_.squeeze(0.2, 0.1, 1)
+        yield "ket on a touched mode"
+        b_.prepare_dm_state(pick(dm), [0])                     # per-entry density matrices
+        b_.beamsplitter(0.5, 0.0, 0, 2)
+        yield "per-entry density matrix"
+        b_.prepare_dm_state(np.outer(k1, k1.conj()), [2])      # one density matrix for all
+        yield "broadcast density matrix"
+        b_.prepare_ket_state(full, [1, 2, 0])                  # whole register, permuted: pure again
+        b_.kerr_interaction(0.2, 2)
+        yield "whole register"
+
+    be = make_backend()
+    be.begin_circuit(n, cutoff_dim=D, batch_size=B)
+    obs = []
+    for e in range(B):
+        ob = OracleBackend()
+        ob.begin_circuit(n, cutoff_dim=D)
+        obs.append((ob, steps(ob, e)))
+    for label in steps(be, None):
+        st = be.state()
+        got = st.dm()
+        for e, (ob, it) in enumerate(obs):
+            assert next(it) == label
+            assert np.abs(got[e] - ob.state().dm()).max() < TOL, (label, e)
+        if label in ("pure two-mode kets", "whole register"):
+            assert st.is_pure
+    with pytest.raises(ValueError, match="Incorrect shape"):
+        be.prepare_ket_state(np.ones((B + 2, D)), [0])
+    with pytest.raises(ValueError, match="multiple times"):
+        be.prepare_ket_state(np.ones((D, D)) / D, [1, 1])
+
+
+def test_batched_general_preparations(monkeypatch):
+    from strawberryfields_b200 import circuit, lib
+    from strawberryfields_b200.backend import B200FockBackend
+
+    monkeypatch.setattr(lib, "_lib", FakeLib())
+    monkeypatch.setattr(circuit, "_TEST_HOST_MODE", True)
+    for lazy in (False, True):
+        def make():
+            be = B200FockBackend()
+            orig = be.begin_circuit
+            be.begin_circuit = lambda n_, **kw: orig(n_, lazy_vacuum=lazy, **kw)
+            return be
+
+        batched_general_preparations(make)

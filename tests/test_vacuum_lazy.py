@@ -275,3 +275,20 @@ def test_full_size_config2_lazy_equals_eager_on_gpu():
     assert abs(res[0][0] - res[1][0]) < TOL
     assert np.abs(res[0][1] - res[1][1]).max() < TOL
     assert np.abs(res[0][2] - res[1][2]).max() < 1e-11
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lazy", [False, True])
+def test_batched_general_preparations_on_gpu(lazy):
+    """GPU variant of tests/test_backend.py::test_batched_general_preparations (written after the round's GPU
+    budget: kept at the very end of the suite so that a surprise here cannot mask the validated tests)."""
+    from strawberryfields_b200.backend import B200FockBackend
+    from test_backend import batched_general_preparations
+
+    def make():
+        be = B200FockBackend()
+        orig = be.begin_circuit
+        be.begin_circuit = lambda n_, **kw: orig(n_, lazy_vacuum=lazy, **kw)
+        return be
+
+    batched_general_preparations(make)
