@@ -1682,7 +1682,7 @@ class DeviceCircuit:
         import numbers
 
         if self._batched:
-            raise NotImplementedError("measure_homodyne on a batched b200fock circuit is not supported yet")
+            return self._measure_homodyne_batched(phi, mode, select, **kwargs)
         self._flush()
         D = self._trunc
         w = 1 / self._hbar  # m omega / hbar
@@ -1750,6 +1750,62 @@ class DeviceCircuit:
                self._stream())
         return np.array([[sample]])
 
+
+    def _measure_homodyne_batched(self, phi, mode, select=None, **kwargs):
+        """Batched homodyne (TF-backend semantics, ``tfbackend/circuit.py:812-941``): every entry is measured on
+        its own.  One device reduction gives the B reduced density matrices; the draws are numpy's, entry by
+        entry in batch order, on the reference Fock backend's grid (``circuit.py:713-801``); the projectors
+        |0><x_phi| differ per entry, so they are applied as ONE per-entry dense table.  ``select``: a number
+        for all entries or an array ``[B]``.  Returns ``[B, 1]``."""
+        self._flush()
+        D, B = self._trunc, self._B
+        w = 1 / self._hbar
+        if select is not None:
+            sel = np.asarray(select)
+            if not np.issubdtype(sel.dtype, np.number) or sel.dtype.kind == "c":
+                raise TypeError("Selected measurement result must be of numeric type.")
+            if sel.shape not in ((), (B,)):
+                raise ValueError("'select' must be a number or have shape (batch_size,)")
+            samples = np.broadcast_to(sel.astype(np.float64), (B,)).copy()
+        else:
+            rho_all = self.reduced_dm_device([mode]).cpu().numpy().reshape(B, D, D)
+            ph = np.exp(-1j * phi * np.arange(D))
+            q_mag = kwargs.get("max", 10)
+            num_bins = kwargs.get("num_bins", 100000)
+            q = np.linspace(-q_mag, q_mag, num_bins)
+            x = np.sqrt(w) * q
+            H = [np.ones_like(x), 2 * x]
+            for i in range(2, D):
+                H.append(2 * x * H[i - 1] - 2 * (i - 1) * H[i - 2])
+            scale = np.array([1 / np.sqrt(2.0 ** n * factorial(n)) for n in range(D)])
+            Hn = np.array(H[:D]) * scale[:, None]
+            env = (w / np.pi) ** 0.5 * np.exp(-w * q ** 2) * (q[1] - q[0])
+            samples = np.zeros(B)
+            for b in range(B):
+                rho = ph[:, None] * rho_all[b] * ph.conj()[None, :]
+                probs = (np.einsum("nm,nq,mq->q", rho, Hn, Hn) * env).real
+                probs /= np.sum(probs)
+                probs[np.abs(probs) < 1e-10] = 0
+                hist = np.random.multinomial(1, probs)
+                samples[b] = q[list(hist).index(1)]
+        inf_sq = np.array([(-0.5) ** (n // 2) * np.sqrt(factorial(n)) / factorial(n // 2) if n % 2 == 0 else 0.0
+                           for n in range(D)], dtype=C128)
+        alpha = samples * np.sqrt(w / 2)
+        disp = self._gen1(L.GATE_DISPLACEMENT, np.abs(alpha), np.angle(alpha + 0j)).cpu().numpy().reshape(B, D, D)
+        eig = np.einsum("n,bnm,m->bn", np.exp(1j * phi * np.arange(D)), disp, inf_sq)
+        proj = np.zeros((B, D, D), dtype=C128)
+        proj[:, 0, :] = eig.conj()
+        self._touch(mode)
+        self._apply_dense_now(torch.from_numpy(proj).to(self.device), mode)
+        self._own()
+        nrm = self._norm_device()
+        if bool((nrm == 0).any().item()):
+            raise ZeroDivisionError("Measurement has zero probability.")
+        per = self._size()
+        for b in range(B):
+            L.call("b200_scale", C.c_void_p(self._buf.data_ptr() + 16 * b * per), per, 1.0, 0.0,
+                   C.c_void_p(nrm.data_ptr() + 8 * b), 1 if self._pure else 0, self._stream())
+        return samples.reshape(B, 1)
 
     def _agree_on(self, value):
         """A sampled outcome every process must share (sharded circuits broadcast rank 0's draw)."""

@@ -406,3 +406,67 @@ def test_batched_general_preparations(monkeypatch):
             return be
 
         batched_general_preparations(make)
+
+
+def batched_homodyne(make_backend):
+    """Batched ``measure_homodyne`` (tfbackend/circuit.py:812-941 semantics on the Fock backend's sampling grid):
+    the B draws in batch order are the draws of B oracle runs made one after the other."""
+    from oracle.fock_oracle import OracleBackend
+
+    D, B, n = 6, 3, 2
+    r = np.array([0.2, 0.5, 0.35])
+    phi = 0.4
+
+    def program(b_, rr):
+        b_.prepare_coherent_state(rr, 0.3, 0)
+        b_.squeeze(0.3, 0.2, 1)
+        b_.beamsplitter(0.6, 0.1, 0, 1)
+
+    for pure in (True, False):
+        be = make_backend()
+        be.begin_circuit(n, cutoff_dim=D, batch_size=B, pure=pure)
+        program(be, r)
+        np.random.seed(17)
+        got = be.measure_homodyne(phi, 0)
+        assert got.shape == (B, 1)
+        post = be.state().dm()
+        np.random.seed(17)
+        for e in range(B):
+            ob = OracleBackend()
+            ob.begin_circuit(n, cutoff_dim=D, pure=pure)
+            program(ob, float(r[e]))
+            want = ob.measure_homodyne(phi, 0)
+            assert abs(float(np.asarray(want).reshape(-1)[0]) - got[e, 0]) < 1e-12
+            assert np.abs(post[e] - ob.state().dm()).max() < TOL
+        # post-selection: one value per entry
+        be.reset(pure=pure)
+        program(be, r)
+        sel = np.array([0.3, -0.2, 1.1])
+        assert np.array_equal(be.measure_homodyne(phi, 1, select=sel), sel.reshape(B, 1))
+        post = be.state().dm()
+        for e in range(B):
+            ob = OracleBackend()
+            ob.begin_circuit(n, cutoff_dim=D, pure=pure)
+            program(ob, float(r[e]))
+            ob.measure_homodyne(phi, 1, select=float(sel[e]))
+            assert np.abs(post[e] - ob.state().dm()).max() < TOL
+    with pytest.raises(ValueError, match="batch_size"):
+        be.measure_homodyne(phi, 0, select=[0.1, 0.2])
+    with pytest.raises(TypeError, match="numeric"):
+        be.measure_homodyne(phi, 0, select="x")
+
+
+def test_batched_homodyne(monkeypatch):
+    from strawberryfields_b200 import circuit, lib
+    from strawberryfields_b200.backend import B200FockBackend
+
+    monkeypatch.setattr(lib, "_lib", FakeLib())
+    monkeypatch.setattr(circuit, "_TEST_HOST_MODE", True)
+    for lazy in (False, True):
+        def make():
+            be = B200FockBackend()
+            orig = be.begin_circuit
+            be.begin_circuit = lambda n_, **kw: orig(n_, lazy_vacuum=lazy, **kw)
+            return be
+
+        batched_homodyne(make)

@@ -292,3 +292,19 @@ def test_batched_general_preparations_on_gpu(lazy):
         return be
 
     batched_general_preparations(make)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lazy", [False, True])
+def test_batched_homodyne_on_gpu(lazy):
+    """GPU variant of tests/test_backend.py::test_batched_homodyne (same placement rule as above)."""
+    from strawberryfields_b200.backend import B200FockBackend
+    from test_backend import batched_homodyne
+
+    def make():
+        be = B200FockBackend()
+        orig = be.begin_circuit
+        be.begin_circuit = lambda n_, **kw: orig(n_, lazy_vacuum=lazy, **kw)
+        return be
+
+    batched_homodyne(make)
