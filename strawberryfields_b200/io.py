@@ -23,7 +23,7 @@ A loaded script is a :class:`CircuitProgram`: the list of operations in the form
 converters consume (``{"op", "args", "kwargs", "modes"}``, ``blackbird_io.py:46-75``).  ``calls()`` lowers
 it to ``BaseFock`` backend calls -- what ``LocalEngine._run_program`` makes after the ``fock`` compiler has
 decomposed the program (``engine.py:422-457``): primitive gates map one to one; ``Xgate``, ``Zgate``,
-``Pgate``, ``CXgate``, ``CZgate``, ``Fouriergate`` use the reference's decompositions
+``Pgate``, ``CXgate``, ``CZgate``, ``Fouriergate``, ``sMZgate`` use the reference's decompositions
 (``ops.py:1726-1732,2149-2158,2209-2216``) and ``Interferometer(U)`` the rectangular (Clements) mesh in the
 reference's gate order (``ops.py:2655-2718``).  ``run(backend)`` executes it and returns the measurement
 samples; ``to_sf()`` builds a ``strawberryfields.Program`` when Strawberry Fields is importable.
@@ -415,21 +415,22 @@ class CircuitProgram:
         return CircuitProgram(self.name, self.version, self.target, ops, self.options)
 
     # ------------------------------------------------------------------ lowering to backend calls
-    def _lower_op(self, op, look):
+    def _lower_op(self, op, look, cutoff=None):
         args = [_resolve(a, look) for a in op.get("args", [])]
         kwargs = {k: _resolve(a, look) for k, a in op.get("kwargs", {}).items()}
-        return lower(op["op"], args, kwargs, op["modes"])
+        return lower(op["op"], args, kwargs, op["modes"], cutoff)
 
-    def calls(self, args=None):
+    def calls(self, args=None, cutoff_dim=None):
         """``[(method, *args)]``: the ``BaseFock`` calls of the program (measurements included, in place).
         ``args`` binds template parameters; a program with measured parameters has no static call list
         (``run`` feeds the outcomes forward)."""
         if self.has_feed_forward:
             raise ValueError("the program uses measured parameters (q<mode>): its calls depend on the outcomes, use run()")
         look = self._lookup(args, {})
+        D = cutoff_dim if cutoff_dim is not None else self.backend_options.get("cutoff_dim")
         out = []
         for op in self.operations:
-            out.extend(self._lower_op(op, look))
+            out.extend(self._lower_op(op, look, D))
         return out
 
     def run(self, backend, cutoff_dim=None, args=None, **begin_options):
@@ -447,7 +448,7 @@ class CircuitProgram:
         samples = {}
         look = self._lookup(args, samples)
         for op in self.operations:
-            for call in self._lower_op(op, look):
+            for call in self._lower_op(op, look, int(D)):
                 ret = getattr(backend, call[0])(*call[1:-1], **call[-1]) if isinstance(call[-1], dict) else \
                     getattr(backend, call[0])(*call[1:])
                 if call[0].startswith("measure_"):
@@ -797,9 +798,10 @@ def _arg(args, kwargs, i, name, default=None):
     return default
 
 
-def lower(op, args, kwargs, modes):
+def lower(op, args, kwargs, modes, cutoff=None):
     """One program operation -> ``BaseFock`` calls.  Gates whose first parameter is zero are skipped, as
-    ``Gate.apply`` does (``ops.py:494-509``)."""
+    ``Gate.apply`` does (``ops.py:494-509``).  ``cutoff``: only ``Catstate`` needs it (its ket is built on the
+    host, ``ops.py:880-922``)."""
     a = lambda i, name, default=None: _arg(args, kwargs, i, name, default)  # noqa: E731
     m = list(modes)
     one = {"Dgate": ("displacement", ("r", "phi")), "Sgate": ("squeeze", ("r", "phi"))}
@@ -838,6 +840,10 @@ def lower(op, args, kwargs, modes):
             if a(0, "theta", math.pi / 4) != 0 else []
     if op == "MZgate":
         return [("mzgate", float(a(0, "phi_in")), float(a(1, "phi_ex")), m[0], m[1])]
+    if op == "sMZgate":  # ops.py:2023-2030
+        bs = ("beamsplitter", math.pi / 4, math.pi / 2, m[0], m[1])
+        rots = [("rotation", float(a(1, "phi_ex")) - math.pi / 2, m[1]), ("rotation", float(a(0, "phi_in")) - math.pi / 2, m[0])]
+        return [bs] + [c for c in rots if c[1] != 0] + [bs]
     if op == "S2gate":
         r = a(0, "r")
         return [] if r == 0 else [("two_mode_squeeze", float(r), float(a(1, "phi", 0.0)), m[0], m[1])]
@@ -885,6 +891,21 @@ def lower(op, args, kwargs, modes):
                  float(a(2, "r_s", 0.0)), float(a(3, "phi_s", 0.0)), m[0])]
     if op == "Thermal":
         return [("prepare_thermal_state", float(a(0, "n", 0.0)), m[0])]
+    if op == "Catstate":  # ops.py:880-922: (|alpha> + e^{i pi p} |-alpha>) / N as a host-built ket
+        if cutoff is None:
+            raise ValueError("Catstate needs the cutoff dimension: calls(cutoff_dim=..) or run()")
+        alpha = float(a(0, "a", 0.0)) * np.exp(1j * float(a(1, "phi", 0.0)))
+        theta = math.pi * float(a(2, "p", 0))
+        l = np.arange(int(cutoff))
+        fact = np.sqrt(np.array([math.factorial(int(x)) for x in l], dtype=float))
+        temp = math.exp(-0.5 * abs(alpha) ** 2)
+        N = temp / math.sqrt(2 * (1 + math.cos(theta) * temp ** 4))
+        ket = (alpha ** l / fact + np.exp(1j * theta) * (-alpha) ** l / fact) * N
+        return [("prepare_ket_state", ket, m)]
+    if op == "GKP":  # ops.py:959-967 -> backend.prepare_gkp(state, epsilon, ampl_cutoff, representation, shape, mode)
+        state = a(0, "state", [0, 0])
+        return [("prepare_gkp", [float(x) for x in state], float(a(1, "epsilon", 0.2)), float(a(2, "ampl_cutoff", 1e-12)),
+                 a(3, "representation", "real"), a(4, "shape", "square"), {"mode": m[0]})]
     if op == "Ket":
         return [("prepare_ket_state", np.asarray(a(0, "state")), m)]
     if op == "DensityMatrix":
