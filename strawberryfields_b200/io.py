@@ -17,7 +17,8 @@ the parts of both languages a Fock-backend program uses:
   ``type`` / ``include`` statements (time-domain programs, out of scope) are refused with
   ``NotImplementedError``.
 * XIR: ``options: .. end;`` and ``constants: .. end;`` blocks, ``use`` / declaration statements (ignored),
-  and statements ``Op(args, key: val) | [wires];``.
+  statements ``Op(args, key: val) | [wires];`` and gate definitions ``gate Name(params)[wires]: .. end;``,
+  expanded in place where they are used (``xir.get_expanded_statements``, ``xir_io.py:89``).
 
 A loaded script is a :class:`CircuitProgram`: the list of operations in the form the reference's
 converters consume (``{"op", "args", "kwargs", "modes"}``, ``blackbird_io.py:46-75``).  ``calls()`` lowers
@@ -662,16 +663,75 @@ def _loads_xir(text):
             text = text[:m.start()] + text[m.end():]
     if "_name_" in prog.options:
         prog.name = prog.options.pop("_name_")
+    if str(prog.options.get("_type_", "")).strip('"') == "tdm":
+        raise NotImplementedError("time-domain (tdm) XIR programs are not supported by the b200fock loader")
+
+    # gate definitions: ``gate Name(params)[wires]: <statements> end;`` (params and wires optional; wires default
+    # to the labels of the body in sorted order).  Expanded in place at every use, as the reference does through
+    # ``xir.get_expanded_statements`` (xir_io.py:89).
+    defs = {}
+
+    def take_def(m):
+        body = [" ".join(x.split()) for x in m.group(4).split(";") if x.strip()]
+        params = [x.strip() for x in m.group(2).split(",")] if m.group(2) and m.group(2).strip() else []
+        wires = [x.strip() for x in m.group(3).split(",")] if m.group(3) and m.group(3).strip() else None
+        defs[m.group(1)] = (params, wires, body)
+        return ""
+
+    text = re.sub(r"\bgate\s+([A-Za-z_]\w*)\s*(?:\(([^)]*)\))?\s*(?:\[([^\]]*)\])?\s*:(.*?)\bend\s*;", take_def, text,
+                  flags=re.S)
+
+    def wire_labels(text_modes):
+        t = text_modes.strip()
+        if t and t[0] in "[(":
+            t = t[1:-1]
+        return [x.strip() for x in _split_top(t) if x.strip()]
+
+    def emit(stmt, scope, wire_map, depth=0):
+        if depth > 32:
+            raise ProgramSyntaxError("gate definitions nest deeper than 32 levels (recursive definition?)")
+        m = _OP_LINE.match(stmt)
+        if not m:
+            raise ProgramSyntaxError("cannot parse XIR statement %r" % stmt)
+        args, kwargs = _parse_args(m.group(2), scope, ":") if m.group(2) and m.group(2).strip() else ([], {})
+        labels = wire_labels(m.group(3))
+        if wire_map is not None:
+            missing = [w for w in labels if w not in wire_map]
+            if missing:
+                raise ProgramSyntaxError("wire(s) %s are not wires of the gate definition" % ", ".join(missing))
+            labels = [str(wire_map[w]) for w in labels]
+        modes = _parse_modes("[" + ", ".join(labels) + "]")
+        if m.group(1) in defs:
+            params, wires, body = defs[m.group(1)]
+            if kwargs:
+                bound = dict(zip(params, args))
+                bound.update(kwargs)
+            else:
+                bound = dict(zip(params, args))
+            if len(args) > len(params) or sorted(bound) != sorted(params):
+                raise ProgramSyntaxError("gate %s takes parameters (%s)" % (m.group(1), ", ".join(params)))
+            if wires is None:
+                seen = []
+                for b in body:
+                    mb = _OP_LINE.match(b)
+                    if mb:
+                        seen += [w for w in wire_labels(mb.group(3)) if w not in seen]
+                wires = sorted(seen, key=lambda w: (0, int(w)) if w.isdigit() else (1, w))
+            if len(wires) != len(modes):
+                raise ProgramSyntaxError("gate %s acts on %d wire(s), applied to %d" % (m.group(1), len(wires), len(modes)))
+            inner_scope = dict(env)
+            inner_scope.update(bound)
+            for b in body:
+                emit(b, inner_scope, dict(zip(wires, modes)), depth + 1)
+            return
+        args = [np.array(a) if isinstance(a, list) else a for a in args]
+        prog.operations.append({"op": m.group(1), "args": args, "kwargs": kwargs, "modes": modes})
+
     for stmt in text.split(";"):
         s = " ".join(stmt.split())
         if not s or s.split()[0] in ("use", "gate", "out", "func", "obs"):
             continue
-        m = _OP_LINE.match(s)
-        if not m:
-            raise ProgramSyntaxError("cannot parse XIR statement %r" % s)
-        args, kwargs = _parse_args(m.group(2), env, ":") if m.group(2) and m.group(2).strip() else ([], {})
-        args = [np.array(a) if isinstance(a, list) else a for a in args]
-        prog.operations.append({"op": m.group(1), "args": args, "kwargs": kwargs, "modes": _parse_modes(m.group(3))})
+        emit(s, env, None)
     return prog
 
 
@@ -697,9 +757,15 @@ def _dumps_xir(prog):
 def loads(s, ir="blackbird"):
     """Load a circuit from a string (``sf.loads``, ``io/__init__.py:145-166``)."""
     if ir == "blackbird":
-        return _loads_blackbird(s)
+        prog = _loads_blackbird(s)
+        if not prog.operations:     # io/__init__.py:50-53: the number of modes of an empty program is unknown
+            raise ValueError("Blackbird program contains no quantum operations!")
+        return prog
     if ir == "xir":
-        return _loads_xir(s)
+        prog = _loads_xir(s)
+        if not prog.operations:     # xir_io.py:78-82
+            raise ValueError("The XIR program is empty and cannot be transformed into a Strawberry Fields program.")
+        return prog
     raise ValueError(f"'{ir}' not recognized as a valid IR option. Valid options are 'xir' and 'blackbird'.")
 
 

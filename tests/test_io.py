@@ -471,3 +471,126 @@ def test_catstate_gkp_smzgate_lower_like_the_reference():
     assert np.abs(ob.state().dm() - want.dm()).max() < 1e-12
     with pytest.raises(ValueError, match="cutoff"):
         bio.loads("Catstate(0.8) | 0").calls()
+
+
+# ------------------------------------------------------------------ the reference's own script tests as golden vectors
+# (tests/frontend/io/test_io_blackbird.py:73-92,386-580 and test_io_xir.py:68-79,470-600: the scripts and what the
+# reference asserts about the converted programs; here checked on the operation list of the loader)
+REF_U = np.array([
+    [0.219546940711 - 0.256534554457j, 0.611076853957 + 0.524178937791j, -0.102700187435 + 0.474478834685j, -0.027250232925 + 0.03729094623j],
+    [0.451281863394 + 0.602582912475j, 0.456952590016 + 0.01230749109j, 0.131625867435 - 0.450417744715j, 0.035283194078 - 0.053244267184j],
+    [0.038710094355 + 0.492715562066j, -0.019212744068 - 0.321842852355j, -0.240776471286 + 0.524432833034j, -0.458388143039 + 0.329633367819j],
+    [-0.156619083736 + 0.224568570065j, 0.109992223305 - 0.163750223027j, -0.421179844245 + 0.183644837982j, 0.818769184612 + 0.068015658737j]])
+
+REF_BLACKBIRD = """\
+name test_program
+version 1.0
+
+complex array A0[4, 4] =
+    0.219546940711-0.256534554457j, 0.611076853957+0.524178937791j, -0.102700187435+0.474478834685j, -0.027250232925+0.03729094623j
+    0.451281863394+0.602582912475j, 0.456952590016+0.01230749109j, 0.131625867435-0.450417744715j, 0.035283194078-0.053244267184j
+    0.038710094355+0.492715562066j, -0.019212744068-0.321842852355j, -0.240776471286+0.524432833034j, -0.458388143039+0.329633367819j
+    -0.156619083736+0.224568570065j, 0.109992223305-0.163750223027j, -0.421179844245+0.183644837982j, 0.818769184612+0.068015658737j
+
+Vacuum() | 1
+Squeezed(0.12, 0.0) | 2
+Sgate(1, 0.0) | 0
+Dgate(0.735934779718964, 0.7469555733762603) | 1
+S2gate(0.543, -0.12) | [0, 3]
+Interferometer(A0) | [0, 1, 2, 3]
+MeasureHomodyne(0) | 0
+MeasureHomodyne(0.43, select=0.32) | 2
+MeasureHomodyne(0.43, select=0.32) | 2
+"""
+
+REF_XIR = """\
+Vacuum | [1];
+Squeezed(0.12, 0.0) | [2];
+Sgate(1, 0.0) | [0];
+Dgate(0.735934779718964, 0.7469555733762603) | [1];
+S2gate(0.543, -0.12) | [0, 3];
+Interferometer([[(0.219546940711-0.256534554457j), (0.611076853957+0.524178937791j), (-0.102700187435+0.474478834685j), (-0.027250232925+0.03729094623j)], [(0.451281863394+0.602582912475j), (0.456952590016+0.01230749109j), (0.131625867435-0.450417744715j), (0.035283194078-0.053244267184j)], [(0.038710094355+0.492715562066j), (-0.019212744068-0.321842852355j), (-0.240776471286+0.524432833034j), (-0.458388143039+0.329633367819j)], [(-0.156619083736+0.224568570065j), (0.109992223305-0.163750223027j), (-0.421179844245+0.183644837982j), (0.818769184612+0.068015658737j)]]) | [0, 1, 2, 3];
+MeasureHomodyne(phi: 0) | [0];
+MeasureHomodyne(phi: 0.43, select: 0.32) | [2];
+MeasureHomodyne(phi: 0.43, select: 0.32) | [2];\
+"""
+
+
+@pytest.mark.parametrize("ir,script", [("blackbird", REF_BLACKBIRD), ("xir", REF_XIR)], ids=["blackbird", "xir"])
+def test_reference_not_compiled_program_scripts(ir, script):
+    """the program of the reference's ``prog`` fixture (test_io_xir.py:46-66) as its two serialisations"""
+    prog = bio.loads(script, ir=ir)
+    assert [op["op"] for op in prog.operations] == ["Vacuum", "Squeezed", "Sgate", "Dgate", "S2gate", "Interferometer",
+                                                    "MeasureHomodyne", "MeasureHomodyne", "MeasureHomodyne"]
+    assert [op["modes"] for op in prog.operations] == [[1], [2], [0], [1], [0, 3], [0, 1, 2, 3], [0], [2], [2]]
+    assert prog.operations[1]["args"] == [0.12, 0.0] and prog.operations[2]["args"] == [1, 0.0]
+    assert np.allclose(prog.operations[3]["args"], [abs(0.54 + 0.5j), np.angle(0.54 + 0.5j)], rtol=0, atol=1e-15)
+    assert prog.operations[4]["args"] == [0.543, -0.12]
+    assert np.array_equal(np.asarray(prog.operations[5]["args"][0]), REF_U)
+    last = prog.operations[8]
+    assert (last["args"] + [last["kwargs"].get("phi")])[0] == 0.43 and last["kwargs"]["select"] == 0.32
+    assert prog.num_subsystems == 4
+    # both serialisations lower to the same backend calls
+    other = bio.loads(REF_XIR if ir == "blackbird" else REF_BLACKBIRD, ir="xir" if ir == "blackbird" else "blackbird")
+    for a, b in zip(prog.calls(), other.calls()):
+        assert a[0] == b[0] and all(np.array_equal(x, y) for x, y in zip(a[1:], b[1:]))
+
+
+def test_reference_blackbird_conversion_cases():
+    indent = lambda text: "\n".join("        " + line for line in text.splitlines())  # noqa: E731  (the reference's are indented)
+    with pytest.raises(ValueError, match="contains no quantum operations"):
+        bio.loads(indent("name test_program\nversion 1.0\n"))
+    prog = bio.loads(indent("name test_program\nversion 1.0\nVac | 0\n"))
+    assert prog.name == "test_program" and prog.operations == [{"op": "Vac", "args": [], "kwargs": {}, "modes": [0]}]
+    assert prog.calls() == [("prepare_vacuum_state", 0)]
+    prog = bio.loads(indent("name test_program\nversion 1.0\n\nDgate(r=0.54, phi=0) | 0\n"))
+    assert prog.operations[0]["kwargs"] == {"r": 0.54, "phi": 0} and prog.calls() == [("displacement", 0.54, 0.0, 0)]
+    prog = bio.loads(indent("name test_program\nversion 1.0\n\nBSgate(theta=0.54, phi=pi) | [0, 2]\n"))
+    assert prog.calls() == [("beamsplitter", 0.54, np.pi, 0, 2)]
+    # test_gate_measured_par
+    prog = bio.loads(indent("name test_program\nversion 1.0\n\nMeasureX | 0\nDgate(q0) | 1\nRgate(2*q0) | 2\n"))
+    p1, p2 = prog.operations[1]["args"][0], prog.operations[2]["args"][0]
+    assert p1.node == ("measured", 0) and p2.measured_modes == [0] and p2.evaluate(lambda k, m: 0.25) == 0.5
+    # test_gate_free_par
+    prog = bio.loads(indent("name test_program\nversion 1.0\n\n"
+                            "Dgate(1-{ALPHA}, 0) | 0     # keyword arg, compound expr\n"
+                            "Rgate(theta={foo_bar1}) | 0  # keyword arg, atomic\n"
+                            "Dgate({ALPHA}**2, 0) | 0        # positional arg, compound expr\n"
+                            "Rgate({foo_bar2}) | 0        # positional arg, atomic\n"))
+    assert set(prog.free_parameters) == {"foo_bar1", "foo_bar2", "ALPHA"} and len(prog.operations) == 4
+    assert prog.operations[1]["kwargs"]["theta"].node == ("free", "foo_bar1")
+    assert prog.operations[3]["args"][0].node == ("free", "foo_bar2")
+    assert prog.calls(args={"ALPHA": 0.5, "foo_bar1": 0.1, "foo_bar2": 0.2}) == [
+        ("displacement", 0.5, 0.0, 0), ("rotation", 0.1, 0), ("displacement", 0.25, 0.0, 0), ("rotation", 0.2, 0)]
+
+
+def test_reference_xir_gate_definitions():
+    """test_io_xir.py:561-600: user-defined gates are expanded in place, wires default to the body's labels"""
+    script = """
+        gate Aubergine(x, y)[w]:
+            Squeezed(x, y) | [w];
+        end;
+
+        gate Banana(a, b, c, d, x, y):
+            Aubergine(x, y) | [0];
+            Aubergine(x, y) | [1];
+            Rgate(a) | [0];
+            BSgate(b, c) | [0, 1];
+            Rgate(d) | [1];
+        end;
+
+        Vacuum | [1];
+        Banana(0.5, 0.4, 0.0, 0.5, 1.0, 0.0) | [3, 0];
+    """
+    prog = bio.loads(script, ir="xir")
+    assert [op["op"] for op in prog.operations] == ["Vacuum", "Squeezed", "Squeezed", "Rgate", "BSgate", "Rgate"]
+    assert [op["args"] for op in prog.operations] == [[], [1.0, 0.0], [1.0, 0.0], [0.5], [0.4, 0.0], [0.5]]
+    assert [op["modes"] for op in prog.operations] == [[1], [3], [0], [3], [3, 0], [0]]
+    with pytest.raises(bio.ProgramSyntaxError, match="acts on 2 wire"):
+        bio.loads(script.replace("| [3, 0];", "| [3];"), ir="xir")
+    with pytest.raises(bio.ProgramSyntaxError, match="takes parameters"):
+        bio.loads(script.replace("Banana(0.5, 0.4, 0.0, 0.5, 1.0, 0.0)", "Banana(0.5)"), ir="xir")
+    with pytest.raises(ValueError, match="XIR program is empty"):
+        bio.loads("options:\n  cutoff_dim: 5;\nend;\n", ir="xir")
+    with pytest.raises(NotImplementedError, match="tdm"):
+        bio.loads("options:\n  _type_: tdm;\n  N: [2, 3];\nend;\nSgate(0.1, 0.0) | [2];", ir="xir")
