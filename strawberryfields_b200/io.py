@@ -735,6 +735,15 @@ def _loads_xir(text):
     return prog
 
 
+def _fmt_xir(v):
+    """XIR writes complex numbers the way Python prints them, in parentheses (test_io_xir.py:68-79)"""
+    if isinstance(v, (np.ndarray, list, tuple)):
+        return "[" + ", ".join(_fmt_xir(x) for x in v) + "]"
+    if isinstance(v, (complex, np.complexfloating)):
+        return str(complex(v))
+    return _fmt(v)
+
+
 def _dumps_xir(prog):
     if any(True for _ in prog._symbols()):
         raise NotImplementedError("free / measured parameters are written as Blackbird only")
@@ -744,13 +753,13 @@ def _dumps_xir(prog):
         opts = {"_name_": prog.name, **opts}
     if opts:
         out.append("options:")
-        out.extend("    %s: %s;" % (k, _fmt(v)) for k, v in opts.items())
+        out.extend("    %s: %s;" % (k, _fmt_xir(v)) for k, v in opts.items())
         out.append("end;")
         out.append("")
     for op in prog.operations:
-        parts = [_fmt(a) for a in op.get("args", [])] + ["%s: %s" % (k, _fmt(v)) for k, v in op.get("kwargs", {}).items()]
+        parts = [_fmt_xir(a) for a in op.get("args", [])] + ["%s: %s" % (k, _fmt_xir(v)) for k, v in op.get("kwargs", {}).items()]
         out.append("%s%s | [%s];" % (op["op"], "(%s)" % ", ".join(parts) if parts else "", ", ".join(map(str, op["modes"]))))
-    return "\n".join(out) + ("\n" if out else "")
+    return "\n".join(out)      # no trailing newline, like xir.Program.serialize()
 
 
 # ------------------------------------------------------------------------------------ public API (io/__init__.py)
@@ -773,6 +782,8 @@ def load(f, ir="blackbird"):
     """Load a circuit from a ``.xbb`` / ``.xir`` file or file object (``sf.load``, ``io/__init__.py:169-237``)."""
     if hasattr(f, "read"):
         return loads(f.read(), ir)
+    if not isinstance(f, (str, os.PathLike)):      # io/__init__.py:226-230
+        raise ValueError("file must be a string, pathlib.Path, or file pointer")
     name = os.fspath(f)
     if ir not in ("blackbird", "xir"):
         raise ValueError(f"'{ir}' not recognized as a valid IR option. Valid options are 'xir' and 'blackbird'.")
@@ -797,6 +808,8 @@ def save(f, prog, ir="blackbird"):
     if hasattr(f, "write"):
         f.write(text)
         return
+    if not isinstance(f, (str, os.PathLike)):      # io/__init__.py:134-138
+        raise ValueError("file must be a string, pathlib.Path, or file pointer")
     name = os.fspath(f)
     ext = ".xbb" if ir == "blackbird" else ".xir"
     if not name.endswith(ext):
@@ -1014,7 +1027,6 @@ def load_state(f, backend=None):
     if backend is not None:
         if backend.get_cutoff_dim() != D or len(backend.get_modes()) != n:
             raise ValueError("checkpoint holds %d modes at cutoff %d; the backend's circuit differs" % (n, D))
-        if getattr(data, "ndim", 0) in (n + 1, 2 * n + 1):
-            raise NotImplementedError("batched checkpoints are loaded entry by entry")
+        # a batched state ([B, ..]) goes back in one call: the leading axis is the batch (tfbackend/circuit.py:343-396)
         (backend.prepare_ket_state if pure else backend.prepare_dm_state)(data, list(range(n)))
     return data, pure

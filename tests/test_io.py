@@ -594,3 +594,43 @@ def test_reference_xir_gate_definitions():
         bio.loads("options:\n  cutoff_dim: 5;\nend;\n", ir="xir")
     with pytest.raises(NotImplementedError, match="tdm"):
         bio.loads("options:\n  _type_: tdm;\n  N: [2, 3];\nend;\nSgate(0.1, 0.0) | [2];", ir="xir")
+
+
+def test_serialisers_reproduce_the_reference_text(tmp_path):
+    """what ``sf.save`` must write for the reference's ``prog`` fixture (test_io_blackbird.py:736-776,
+    test_io_xir.py:658-700), file-name handling included"""
+    assert bio.loads(REF_BLACKBIRD).serialize() == REF_BLACKBIRD
+    assert bio.loads(REF_XIR, ir="xir").serialize("xir") == REF_XIR
+    prog = bio.loads(REF_BLACKBIRD)
+    bio.save(tmp_path / "test.xbb", prog)                       # path object
+    assert (tmp_path / "test.xbb").read_text() == REF_BLACKBIRD
+    bio.save(str(tmp_path / "test.txt"), prog, ir="xir")        # extension appended
+    xprog = bio.load(str(tmp_path / "test.txt.xir"), ir="xir")
+    assert [op["op"] for op in xprog.operations] == [op["op"] for op in prog.operations]
+    with open(tmp_path / "obj.xbb", "w") as f:                  # file object
+        bio.save(f, prog)
+    with open(tmp_path / "obj.xbb") as f:
+        assert bio.load(f).serialize() == REF_BLACKBIRD
+    for fn in (bio.load, lambda x: bio.save(x, prog)):
+        with pytest.raises(ValueError, match="must be a string, path"):
+            fn(1)
+
+
+def test_batched_state_checkpoint_round_trip(host, tmp_path):
+    from strawberryfields_b200.backend import B200FockBackend
+
+    B, D, n = 3, 4, 2
+    for pure in (True, False):
+        be = B200FockBackend()
+        be.begin_circuit(n, cutoff_dim=D, batch_size=B, pure=pure)
+        be.prepare_coherent_state(np.array([0.1, 0.3, 0.5]), 0.2, 0)
+        be.squeeze(0.2, 0.0, 1)
+        be.beamsplitter(np.array([0.3, 0.6, 0.9]), 0.1, 0, 1)
+        st = be.state()
+        path = str(tmp_path / ("b%d.npz" % pure))
+        bio.save_state(path, st)
+        b2 = B200FockBackend()
+        b2.begin_circuit(n, cutoff_dim=D, batch_size=B)
+        data, was_pure = bio.load_state(path, b2)
+        assert was_pure == st.is_pure and data.shape[0] == B
+        assert b2.state().is_pure == st.is_pure and np.abs(b2.state().data - st.data).max() < 1e-15
