@@ -27,7 +27,8 @@ decomposed the program (``engine.py:422-457``): primitive gates map one to one; 
 ``Pgate``, ``CXgate``, ``CZgate``, ``Fouriergate``, ``sMZgate`` use the reference's decompositions
 (``ops.py:1726-1732,2149-2158,2209-2216``) and ``Interferometer(U)`` the rectangular (Clements) mesh in the
 reference's gate order (``ops.py:2655-2718``).  ``run(backend)`` executes it and returns the measurement
-samples; ``to_sf()`` builds a ``strawberryfields.Program`` when Strawberry Fields is importable.
+samples; ``to_sf()`` builds a ``strawberryfields.Program`` when Strawberry Fields is importable and ``from_sf(prog)``
+goes the other way (``io.to_blackbird``, ``blackbird_io.py:164-232``).
 
 State checkpoints (``save_state`` / ``load_state``) are ``.npz`` files with the ket or density matrix in
 the reference's layout (``backend.py:50-56``) plus cutoff, purity and mode count; a state object of a
@@ -488,6 +489,82 @@ class CircuitProgram:
     # ------------------------------------------------------------------ serialisation
     def serialize(self, ir="blackbird"):
         return dumps(self, ir)
+
+
+def _from_sympy(expr):
+    """sympy expression over the reference's ``FreeParameter`` / ``MeasuredParameter`` atoms -> :class:`Parameter`
+    (or a plain number): the direction ``to_blackbird`` needs (``blackbird_io.py:213-222``)."""
+    import sympy
+
+    def walk(e):
+        if getattr(e, "is_Symbol", False):
+            if hasattr(e, "regref"):
+                return ("measured", int(e.regref.ind))
+            return ("free", str(e.name))
+        if e.is_Number or e.is_NumberSymbol or e == sympy.I:
+            c = complex(e)
+            if e.is_Integer:
+                return int(e)
+            return c.real if c.imag == 0 else c
+        if e.is_Add or e.is_Mul:
+            sym = "+" if e.is_Add else "*"
+            kids = [walk(a) for a in e.args]
+            if sym == "*" and kids[0] == -1 and len(kids) > 1:     # sympy writes -x as (-1)*x
+                rest = kids[1]
+                for k in kids[2:]:
+                    rest = ("bin", "*", rest, k)
+                return ("neg", rest) if isinstance(rest, tuple) else -rest
+            out = kids[0]
+            for k in kids[1:]:
+                out = ("bin", sym, out, k)
+            return out
+        if e.is_Pow:
+            base, ex = walk(e.args[0]), walk(e.args[1])
+            if ex == 0.5:
+                return ("call", "sqrt", (base,))
+            return ("bin", "**", base, ex)
+        if e.is_Function:
+            name = {"Abs": "abs", "asin": "arcsin", "acos": "arccos", "atan": "arctan", "atan2": "arctan2",
+                    "asinh": "arcsinh", "acosh": "arccosh", "atanh": "arctanh"}.get(type(e).__name__, type(e).__name__)
+            if name not in _FUNCS:
+                raise NotImplementedError("function %s has no Blackbird counterpart" % name)
+            return ("call", name, tuple(walk(a) for a in e.args))
+        raise NotImplementedError("cannot convert the symbolic parameter %r" % (e,))
+
+    node = walk(sympy.sympify(expr))
+    return Parameter(node) if isinstance(node, tuple) else node
+
+
+def from_sf(prog, version="1.0"):
+    """A ``strawberryfields.Program`` as a :class:`CircuitProgram` -- the operation list ``io.to_blackbird``
+    builds (``blackbird_io.py:164-232``: measurement ``select`` / ``dark_counts`` as keyword arguments, symbolic
+    parameters kept symbolic), so that ``save(f, from_sf(prog))`` writes what ``sf.save(f, prog)`` writes."""
+    out = CircuitProgram(name=prog.name, version=version)
+    if getattr(prog, "target", None) is not None:
+        opts = dict(prog.run_options or {})
+        opts.update(prog.backend_options or {})
+        out.target = {"name": prog.target, "options": opts}
+
+    def conv(a):
+        if isinstance(a, np.ndarray) and a.dtype == object:
+            return np.array([conv(x) for x in a.flat], dtype=object).reshape(a.shape)
+        if hasattr(a, "free_symbols") or hasattr(a, "is_Symbol"):
+            return _from_sympy(a)
+        return a
+
+    for cmd in prog.circuit:
+        op = {"op": cmd.op.__class__.__name__, "modes": [r.ind for r in cmd.reg], "args": [], "kwargs": {}}
+        if "Measure" in op["op"]:
+            if cmd.op.select is not None:
+                op["kwargs"]["select"] = cmd.op.select
+            if cmd.op.p:
+                op["args"] = [conv(a) for a in cmd.op.p]
+            if op["op"] == "MeasureFock" and getattr(cmd.op, "dark_counts", None) is not None:
+                op["kwargs"]["dark_counts"] = cmd.op.dark_counts
+        else:
+            op["args"] = [conv(a) for a in cmd.op.p]
+        out.operations.append(op)
+    return out
 
 
 # ---------------------------------------------------------------------------------------- Blackbird

@@ -634,3 +634,67 @@ def test_batched_state_checkpoint_round_trip(host, tmp_path):
         data, was_pure = bio.load_state(path, b2)
         assert was_pure == st.is_pure and data.shape[0] == B
         assert b2.state().is_pure == st.is_pure and np.abs(b2.state().data - st.data).max() < 1e-15
+
+
+@pytest.mark.reference
+def test_from_sf_writes_what_the_reference_saves():
+    """``from_sf`` == ``io.to_blackbird`` (blackbird_io.py:164-232) on the reference's own cases
+    (test_io_blackbird.py:43-70,98-350): the ``prog`` fixture must serialise to the text ``sf.save`` writes."""
+    from oracle import ref_shim
+
+    sf = ref_shim.install()
+    from strawberryfields import ops
+    from strawberryfields.parameters import par_funcs as pf
+
+    prog = sf.Program(4, name="test_program")
+    with prog.context as q:
+        ops.Vac | q[1]
+        ops.Squeezed(0.12) | q[2]
+        ops.Sgate(1) | q[0]
+        ops.Dgate(np.abs(0.54 + 0.5j), np.angle(0.54 + 0.5j)) | q[1]
+        ops.S2gate(0.543, -0.12) | (q[0], q[3])
+        ops.Interferometer(REF_U) | q
+        ops.MeasureX | q[0]
+        ops.MeasureHomodyne(0.43, select=0.32) | q[2]
+        ops.MeasureHomodyne(phi=0.43, select=0.32) | q[2]
+    cp = bio.from_sf(prog)
+    assert cp.serialize() == REF_BLACKBIRD
+    assert cp.target["name"] is None and cp.version == "1.0"
+    # measurement keyword arguments
+    prog = sf.Program(1)
+    with prog.context as q:
+        ops.MeasureFock(select=2) | q[0]
+    assert bio.from_sf(prog).operations[0] == {"op": "MeasureFock", "modes": [0], "args": [], "kwargs": {"select": [2]}}
+    prog = sf.Program(1)
+    with prog.context as q:
+        ops.MeasureFock(dark_counts=2) | q[0]
+    assert bio.from_sf(prog).operations[0]["kwargs"] == {"dark_counts": [2]}
+    # symbolic parameters (test_measured_par_str / test_free_par_str)
+    prog = sf.Program(2)
+    with prog.context as q:
+        ops.Sgate(0.43) | q[0]
+        ops.MeasureX | q[0]
+        ops.Zgate(2 * pf.sin(q[0].par)) | q[1]
+    last = bio.from_sf(prog).operations[-1]
+    assert last["op"] == "Zgate" and last["modes"] == [1] and last["args"][0].measured_modes == [0]
+    assert abs(last["args"][0].evaluate(lambda k, m: 0.3) - 2 * np.sin(0.3)) < 1e-15
+    prog = sf.Program(2)
+    r, alpha = prog.params("r", "alpha")
+    with prog.context as q:
+        ops.Sgate(r) | q[0]
+        ops.Zgate(3 * pf.log(-alpha)) | q[1]
+    cp = bio.from_sf(prog)
+    assert cp.operations[0]["args"][0].node == ("free", "r") and cp.operations[0]["args"][1] == 0.0
+    assert cp.free_parameters == ["alpha", "r"]
+    assert abs(cp.operations[1]["args"][0].evaluate(lambda k, n: -0.7) - 3 * np.log(0.7)) < 1e-15
+    # .. and the text loads back to the same expression
+    again = bio.loads(cp.serialize())
+    assert abs(again.operations[1]["args"][0].evaluate(lambda k, n: -0.7) - 3 * np.log(0.7)) < 1e-15
+    # a compiled program carries its target and options
+    prog = sf.Program(2, name="c")
+    with prog.context as q:
+        ops.Pgate(0.43) | q[0]
+        ops.BSgate(0.3, 0.1) | (q[0], q[1])
+    comp = bio.from_sf(prog.compile(compiler="fock", shots=7))
+    assert comp.target == {"name": "fock", "options": {"shots": 7}}
+    assert [op["op"] for op in comp.operations] == ["Sgate", "Rgate", "BSgate"]
