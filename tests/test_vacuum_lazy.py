@@ -308,3 +308,33 @@ def test_batched_homodyne_on_gpu(lazy):
         return be
 
     batched_homodyne(make)
+
+
+@pytest.mark.gpu
+def test_stored_programs_on_gpu():
+    """A Blackbird template with measured parameters through ``CircuitProgram.run`` on the CUDA path (plugin
+    defaults) against the same calls on the oracle -- same seed, same outcomes, same state."""
+    from strawberryfields_b200 import io as bio
+    from strawberryfields_b200.backend import B200FockBackend
+
+    script = ("name ff\nversion 1.0\ntarget fock (cutoff_dim=6)\n"
+              "Fock(2) | 0\nSqueezed({r}, 0.0) | 1\nBSgate(0.7, 0.3) | [0, 1]\nMeasureFock() | 0\n"
+              "Rgate(q0*pi/3) | 1\nDgate(0.1*q0 + 0.05, 0.0) | 2\nMeasureFock() | 1\nRgate(q0 - q1) | 2\n")
+    prog = bio.loads(script)
+    for seed in (3, 11):
+        be = B200FockBackend()
+        np.random.seed(seed)
+        samples = prog.run(be, args={"r": 0.6})
+        ob = OracleBackend()
+        ob.begin_circuit(3, cutoff_dim=6)
+        np.random.seed(seed)
+        ob.prepare_fock_state(2, 0)
+        ob.prepare_squeezed_state(0.6, 0.0, 1)
+        ob.beamsplitter(0.7, 0.3, 0, 1)
+        n0 = int(np.asarray(ob.measure_fock([0])).reshape(-1)[0])
+        ob.rotation(n0 * np.pi / 3, 1)
+        ob.displacement(0.1 * n0 + 0.05, 0.0, 2)
+        n1 = int(np.asarray(ob.measure_fock([1])).reshape(-1)[0])
+        ob.rotation(n0 - n1, 2)
+        assert samples == {0: [n0], 1: [n1]}
+        assert np.abs(be.state().dm() - ob.state().dm()).max() < TOL
