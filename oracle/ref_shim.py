@@ -109,6 +109,40 @@ def install():
         float(r), float(theta), int(cutoff)
     ).copy()
 
+    # thewalrus.symplectic: the four index / rotation helpers the reference's state classes and its own tests
+    # import (backends/states.py:29-30, decompositions.py:25, tests/backend/test_states_polyquad.py:22-23).
+    # Their published definitions (thewalrus 0.22 docs): R(theta) = [[cos, -sin], [sin, cos]];
+    # Omega = [[0, I], [-I, 0]]; xpxp <-> xxpp reorders (x_1, p_1, .., x_N, p_N) <-> (x_1..x_N, p_1..p_N).
+    import numpy as np
+
+    sy = sys.modules["thewalrus.symplectic"]
+
+    def rotation(theta):
+        c, s = np.cos(theta), np.sin(theta)
+        return np.array([[c, -s], [s, c]])
+
+    def sympmat(N, dtype=np.float64):
+        eye, zero = np.identity(N, dtype=dtype), np.zeros((N, N), dtype=dtype)
+        return np.block([[zero, eye], [-eye, zero]])
+
+    def _reorder(S, ind):
+        S = np.asarray(S)
+        if S.shape[0] % 2:
+            raise ValueError("The input array is not even-dimensional")
+        if S.ndim == 2 and S.shape[0] != S.shape[1]:
+            raise ValueError("The input matrix is not square")
+        return S[ind] if S.ndim == 1 else S[:, ind][ind]
+
+    def xpxp_to_xxpp(S):
+        n = np.asarray(S).shape[0]
+        return _reorder(S, np.concatenate([np.arange(0, n, 2), np.arange(1, n, 2)]))
+
+    def xxpp_to_xpxp(S):
+        n = np.asarray(S).shape[0]
+        return _reorder(S, np.arange(n).reshape(2, -1).T.flatten())
+
+    sy.rotation, sy.sympmat, sy.xpxp_to_xxpp, sy.xxpp_to_xpxp = rotation, sympmat, xpxp_to_xxpp, xxpp_to_xpxp
+
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
     import strawberryfields as sf  # noqa: E402
