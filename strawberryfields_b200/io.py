@@ -188,6 +188,7 @@ class Parameter:
         return "Parameter(%s)" % self.text
 
 
+_XIR_NAMES = "__xir_names__"     # env key: unknown names are free parameters (XIR scripts)
 _FREE_PREFIX = "_b200_free_"   # ``{name}`` is rewritten to this prefix + name so that ``ast`` can parse the expression
 
 
@@ -238,6 +239,8 @@ def _eval(expr, env):
                 return _CONSTS[node.id]
             if node.id.startswith(_FREE_PREFIX):
                 return Parameter.free(node.id[len(_FREE_PREFIX):])
+            if env.get(_XIR_NAMES):   # XIR has no {name} syntax: a name that is not a constant is a free parameter
+                return Parameter.free(node.id)      # (io.to_xir writes them so, xir_io.py:287-303)
             if re.fullmatch(r"q\d+", node.id):
                 return Parameter.measured(int(node.id[1:]))
             raise NameError("name %r is not defined in the script" % node.id)
@@ -341,6 +344,7 @@ class CircuitProgram:
         self.target = target or {"name": None, "options": {}}
         self.operations = list(operations or [])
         self.options = dict(options or {})     # XIR options (cutoff_dim, shots, ..)
+        self._bare = set()                     # indices of operations written without an argument list
 
     @property
     def num_subsystems(self):
@@ -667,6 +671,8 @@ def _loads_blackbird(text):
             if not m:
                 raise ProgramSyntaxError("cannot parse line %d: %r" % (i, s))
             args, kwargs = _parse_args(m.group(2), env, "=") if m.group(2) and m.group(2).strip() else ([], {})
+            if m.group(2) is None:      # written without parentheses (``Vac | 0``): an instance, not a call, in the
+                prog._bare.add(len(prog.operations))   # reference front end (blackbird_io.py:63-77)
             prog.operations.append({"op": m.group(1), "args": args, "kwargs": kwargs, "modes": _parse_modes(m.group(3))})
     return prog
 
@@ -720,7 +726,7 @@ def _dumps_blackbird(prog):
 def _loads_xir(text):
     text = re.sub(r"//[^\n]*", "", text)
     prog = CircuitProgram(version="0.1.0")
-    env = {}
+    env = {_XIR_NAMES: True}
     for kind in ("options", "constants"):
         m = re.search(r"\b%s\s*:(.*?)\bend\s*;" % kind, text, re.S)
         if m:
@@ -733,6 +739,10 @@ def _loads_xir(text):
                         if kind != "options":
                             raise
                         val = v.strip().strip('"')  # option values may be bare names (_name_: my_program)
+                    if _symbolic(val):
+                        if kind != "options":
+                            raise NameError("constant %s refers to an undefined name: %s" % (k.strip(), v.strip()))
+                        val = v.strip().strip('"')
                     if kind == "options":
                         prog.options[k.strip()] = val
                     else:
@@ -813,7 +823,12 @@ def _loads_xir(text):
 
 
 def _fmt_xir(v):
-    """XIR writes complex numbers the way Python prints them, in parentheses (test_io_xir.py:68-79)"""
+    """XIR writes complex numbers the way Python prints them, in parentheses (test_io_xir.py:68-79), and free
+    parameters as bare names (xir_io.py:287-303)"""
+    if isinstance(v, Parameter):
+        if v.measured_modes:
+            raise NotImplementedError("measured parameters are written as Blackbird only")
+        return re.sub(r"\{([A-Za-z_]\w*)\}", r"\1", v.text)
     if isinstance(v, (np.ndarray, list, tuple)):
         return "[" + ", ".join(_fmt_xir(x) for x in v) + "]"
     if isinstance(v, (complex, np.complexfloating)):
@@ -822,8 +837,6 @@ def _fmt_xir(v):
 
 
 def _dumps_xir(prog):
-    if any(True for _ in prog._symbols()):
-        raise NotImplementedError("free / measured parameters are written as Blackbird only")
     out = []
     opts = dict(prog.options)
     if prog.name:

@@ -1,0 +1,133 @@
+"""Test infrastructure (build container only): a stand-in for the third-party ``blackbird`` package, built on
+``strawberryfields_b200.io``, so that the REFERENCE's own I/O code and tests run on our parser / writer.
+
+The reference loads and saves programs through ``blackbird.loads`` / ``blackbird.BlackbirdProgram.serialize``
+(``strawberryfields/io/__init__.py:145-237``, ``io/blackbird_io.py:30-232``); the package is not in this image.
+With this facade in ``sys.modules`` (``install()``; ``tests/b200_ref_io_plugin.py`` does it before the
+reference's conftest is imported) ``sf.load`` / ``sf.loads`` / ``sf.save`` / ``io.to_blackbird`` /
+``io.to_program`` are the reference's unmodified code, and every Blackbird script they read or write goes
+through ``strawberryfields_b200.io`` -- which is what the reference's ``tests/frontend/io/test_io_blackbird.py``
+then checks.  Only the attributes the reference touches are provided.  Time-domain programs (``type tdm``)
+are out of scope: the facade raises ``NotImplementedError`` for them.
+"""
+import sys
+import types
+
+import numpy as np
+
+from strawberryfields_b200 import io as bio
+
+
+def _sympy_funcs():
+    import sympy
+
+    names = {"sqrt": sympy.sqrt, "sin": sympy.sin, "cos": sympy.cos, "tan": sympy.tan, "exp": sympy.exp,
+             "log": sympy.log, "arcsin": sympy.asin, "arccos": sympy.acos, "arctan": sympy.atan,
+             "arctan2": sympy.atan2, "asin": sympy.asin, "acos": sympy.acos, "atan": sympy.atan,
+             "sinh": sympy.sinh, "cosh": sympy.cosh, "tanh": sympy.tanh, "arcsinh": sympy.asinh,
+             "arccosh": sympy.acosh, "arctanh": sympy.atanh, "abs": sympy.Abs}
+    return names
+
+
+def _to_sympy(v):
+    """our symbolic parameters -> sympy expressions over plain Symbols, as blackbird hands them to
+    ``parameters.par_convert`` (``parameters.py:249-275``: ``q<n>`` = measured, anything else = free)"""
+    import sympy
+
+    if isinstance(v, bio.Parameter):
+        return v.evaluate(lambda kind, key: sympy.Symbol(key if kind == "free" else "q%d" % key), _sympy_funcs())
+    if isinstance(v, np.ndarray) and v.dtype == object:
+        return np.array([_to_sympy(x) for x in v.flat], dtype=object).reshape(v.shape)
+    return v
+
+
+class RegRefTransform:
+    """a measured-parameter expression (``blackbird.RegRefTransform``): ``expr``, ``func_str``, ``regrefs``"""
+
+    def __init__(self, expr):
+        import sympy
+
+        self.expr = sympy.sympify(expr)
+        self.func_str = str(self.expr)
+        self.regrefs = sorted(int(s.name[1:]) for s in self.expr.free_symbols if s.name[0] == "q" and s.name[1:].isdigit())
+
+    def __str__(self):
+        return self.func_str
+
+
+class BlackbirdProgram:
+    """the container ``io.to_blackbird`` fills and ``io.to_program`` reads (``blackbird_io.py:174-232,43-85``)"""
+
+    def __init__(self, name="blackbird_program", version="1.0"):
+        self._name, self._version = name, version
+        self._target = {"name": None, "options": {}}
+        self._type = {"name": None, "options": {}}
+        self._modes = set()
+        self._operations = []
+        self._var = {}
+
+    name = property(lambda self: self._name)
+    version = property(lambda self: self._version)
+    target = property(lambda self: self._target)
+    programtype = property(lambda self: self._type)
+    operations = property(lambda self: self._operations)
+    modes = property(lambda self: self._modes)
+
+    def is_template(self):
+        return any(bio._symbolic(_from_reference(a)) for op in self._operations
+                   for a in list(op.get("args", [])) + list(op.get("kwargs", {}).values()))
+
+    def serialize(self):
+        if self._type["name"] is not None:
+            raise NotImplementedError("time-domain Blackbird programs are out of scope for b200fock's io")
+        prog = bio.CircuitProgram(name=self._name, version=self._version, target=self._target)
+        for op in self._operations:
+            prog.operations.append({"op": op["op"], "modes": list(op["modes"]),
+                                    "args": [_from_reference(a) for a in op.get("args", [])],
+                                    "kwargs": {k: _from_reference(a) for k, a in op.get("kwargs", {}).items()}})
+        return bio.dumps(prog)
+
+
+def _from_reference(a):
+    """what ``to_blackbird`` puts into the operation list -> our parameters: ``RegRefTransform`` objects and the
+    strings it makes of free-parameter expressions (``blackbird_io.py:213-222``: ``"{r}"``, ``"3*log(-{alpha})"``)"""
+    if isinstance(a, RegRefTransform):
+        return bio._from_sympy(a.expr)
+    if isinstance(a, str) and "{" in a:
+        return bio._eval(a, {})
+    if hasattr(a, "free_symbols"):
+        return bio._from_sympy(a)
+    return a
+
+
+def loads(text):
+    prog = bio._loads_blackbird(text)
+    bb = BlackbirdProgram(name=prog.name, version=prog.version)
+    bb._target = {"name": prog.target.get("name"), "options": dict(prog.target.get("options", {}))}
+    bare = getattr(prog, "_bare", set())
+    for i, op in enumerate(prog.operations):
+        entry = {"op": op["op"], "modes": list(op["modes"])}
+        if i not in bare:   # ``Vac | 0`` carries no argument lists, ``Vacuum() | 0`` empty ones (blackbird_io.py:63-77)
+            entry["args"] = [_to_sympy(a) for a in op["args"]]
+            entry["kwargs"] = {k: _to_sympy(a) for k, a in op["kwargs"].items()}
+        bb._operations.append(entry)
+        bb._modes |= set(op["modes"])
+    return bb
+
+
+def load(filename):
+    with open(filename, "r") as f:
+        return loads(f.read())
+
+
+def install():
+    """put the facade where ``import blackbird`` finds it (keeps the submodule stubs of oracle/ref_shim.py)"""
+    mod = sys.modules.get("blackbird")
+    if mod is None:
+        mod = sys.modules["blackbird"] = types.ModuleType("blackbird")
+    mod.BlackbirdProgram = BlackbirdProgram
+    mod.RegRefTransform = RegRefTransform
+    mod.loads = loads
+    mod.load = load
+    mod.__version__ = "b200fock-io-facade"
+    return mod

@@ -321,8 +321,9 @@ def test_template_parameters_stay_symbolic_until_bound():
     # written back as Blackbird and loaded again: the same script
     assert bio.loads(prog.serialize()).serialize() == prog.serialize()
     assert "{alpha}" in prog.serialize() and "sqrt({r})" in prog.serialize()
-    with pytest.raises(NotImplementedError):
-        prog.serialize("xir")
+    # XIR has no {name} syntax: free parameters are bare names there (io.to_xir writes them so, xir_io.py:287-303)
+    xprog = bio.loads(prog.serialize("xir"), ir="xir")
+    assert "Sgate(r, 0.1) | [0];" in prog.serialize("xir") and xprog.free_parameters == prog.free_parameters
     with pytest.raises(ValueError, match="alpha"):
         prog.calls(args={"r": 0.2, "theta": 0.1})
     vals = {"r": 0.25, "alpha": 0.5, "theta": 0.4}
@@ -335,6 +336,9 @@ def test_template_parameters_stay_symbolic_until_bound():
     assert part.free_parameters == ["alpha", "theta"] and part.operations[0]["args"][0] == 0.25
     assert part.operations[1]["kwargs"]["phi"] == 0.5 and "{r}" not in part.serialize()
     assert part.bind(alpha=0.5, theta=0.4).calls() == calls
+    assert xprog.calls(args=vals) == calls
+    with pytest.raises(NotImplementedError, match="measured parameters"):
+        bio.loads("MeasureFock() | 0\nRgate(q0) | 1").serialize("xir")
     with pytest.raises(ValueError, match="no free parameter"):
         prog.bind(gamma=1.0)
 
