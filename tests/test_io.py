@@ -702,3 +702,62 @@ def test_from_sf_writes_what_the_reference_saves():
     comp = bio.from_sf(prog.compile(compiler="fock", shots=7))
     assert comp.target == {"name": "fock", "options": {"shots": 7}}
     assert [op["op"] for op in comp.operations] == ["Sgate", "Rgate", "BSgate"]
+
+
+@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("ir", ["blackbird", "xir"])
+def test_random_programs_round_trip(seed, ir):
+    """write -> read -> write is a fixed point and keeps every number bit for bit (repr round trip), for random
+    programs over the whole operation set incl. arrays, keyword arguments, free parameters and expressions"""
+    rs = np.random.RandomState(100 + seed)
+    n = int(rs.randint(2, 6))
+    free = [bio.Parameter.free(nm) for nm in ("alpha", "beta_1", "G")]
+
+    def number():
+        kind = rs.randint(5)
+        if kind == 0:
+            return int(rs.randint(-3, 4))
+        if kind == 1:
+            return float(rs.randn() * 10.0 ** rs.randint(-8, 8))
+        if kind == 2:
+            p = free[rs.randint(3)]
+            return [p, 2 * p - 0.5, p ** 2 / 3, -p, bio.Parameter.call("sin", [p]) * 1.5][rs.randint(5)]
+        return float(rs.uniform(-1, 1))
+
+    ops1 = ["Sgate", "Dgate", "Rgate", "Kgate", "Vgate", "Xgate", "Zgate", "Pgate", "LossChannel", "Coherent", "Squeezed"]
+    ops2 = ["BSgate", "S2gate", "MZgate", "CKgate", "CXgate", "CZgate"]
+    prog = bio.CircuitProgram(name="fuzz_%d" % seed, target={"name": "fock", "options": {"cutoff_dim": 5, "shots": 3}}
+                              if ir == "blackbird" else None, options={"cutoff_dim": 5} if ir == "xir" else None)
+    for _ in range(int(rs.randint(5, 25))):
+        r = rs.rand()
+        if r < 0.5:
+            nargs = int(rs.randint(1, 3))
+            prog.operations.append({"op": ops1[rs.randint(len(ops1))], "args": [number() for _ in range(nargs)], "kwargs": {},
+                                    "modes": [int(rs.randint(n))]})
+        elif r < 0.85:
+            a, b = rs.choice(n, 2, replace=False)
+            kw = {"phi": number()} if rs.rand() < 0.3 else {}
+            prog.operations.append({"op": ops2[rs.randint(len(ops2))], "args": [number()], "kwargs": kw, "modes": [int(a), int(b)]})
+        elif r < 0.93:
+            k = int(rs.randint(2, n + 1))
+            U = np.linalg.qr(rs.randn(k, k) + 1j * rs.randn(k, k))[0]
+            prog.operations.append({"op": "Interferometer", "args": [U], "kwargs": {}, "modes": [int(x) for x in rs.permutation(n)[:k]]})
+        else:
+            prog.operations.append({"op": "MeasureFock", "args": [], "kwargs": {"select": [int(rs.randint(3))]} if rs.rand() < 0.5 else {},
+                                    "modes": [int(rs.randint(n))]})
+    text = bio.dumps(prog, ir)
+    again = bio.loads(text, ir)
+    assert bio.dumps(again, ir) == text
+    assert len(again.operations) == len(prog.operations) and again.free_parameters == prog.free_parameters
+    look = lambda kind, key: {"alpha": 0.3, "beta_1": -1.2, "G": 2.5}[key]  # noqa: E731
+    for a, b in zip(prog.operations, again.operations):
+        assert a["op"] == b["op"] and a["modes"] == b["modes"] and sorted(a["kwargs"]) == sorted(b["kwargs"])
+        for x, y in zip(a["args"] + [a["kwargs"][k] for k in sorted(a["kwargs"])],
+                        b["args"] + [b["kwargs"][k] for k in sorted(b["kwargs"])]):
+            x, y = bio._resolve(x, look), bio._resolve(y, look)
+            if isinstance(x, np.ndarray):
+                assert np.array_equal(x, np.asarray(y))
+            elif isinstance(x, float):
+                assert np.isclose(x, y, rtol=1e-15, atol=0)     # expressions re-associate constants at most
+            else:
+                assert x == y
