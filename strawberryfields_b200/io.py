@@ -345,6 +345,8 @@ class CircuitProgram:
         self.operations = list(operations or [])
         self.options = dict(options or {})     # XIR options (cutoff_dim, shots, ..)
         self._bare = set()                     # indices of operations written without an argument list
+        self.programtype = {"name": None, "options": {}}   # Blackbird ``type`` line / XIR ``_type_`` option
+        self.variables = {}                    # time-domain programs: the looped-over arrays p0, p1, .. by name
 
     @property
     def num_subsystems(self):
@@ -636,7 +638,15 @@ def _loads_blackbird(text):
                     args, kwargs = _parse_args(mm.group(2), scope, "=") if mm.group(2) and mm.group(2).strip() else ([], {})
                     prog.operations.append({"op": mm.group(1), "args": args, "kwargs": kwargs,
                                             "modes": _parse_modes(mm.group(3), scope)})
-        elif head[0] in ("type", "include"):
+        elif head[0] == "type":
+            # ``type tdm (temporal_modes=3)``: parsed so that the script can be inspected and converted by a front
+            # end; ``loads`` refuses to hand a time-domain program to the Fock backend
+            m = re.match(r"^type\s+([\w.\-]+)\s*(?:\((.*)\))?\s*$", s)
+            if not m:
+                raise ProgramSyntaxError("bad type line: %r" % s)
+            opts = _parse_args(m.group(2), env, "=")[1] if m.group(2) else {}
+            prog.programtype = {"name": m.group(1), "options": opts}
+        elif head[0] == "include":
             raise NotImplementedError("Blackbird %r statements are not supported by the b200fock loader" % head[0])
         elif head[0] in _TYPES and len(head) > 1 and "=" in s and "|" not in s.split("=", 1)[0]:
             rest = head[1]
@@ -659,7 +669,12 @@ def _loads_blackbird(text):
                         arr = arr.reshape(shape)
                     if list(arr.shape) != shape:
                         raise ProgramSyntaxError("array %s has shape %r, declared %r" % (m.group(1), arr.shape, shape))
-                env[m.group(1)] = arr
+                if prog.programtype["name"] == "tdm" and re.fullmatch(r"p\d+", m.group(1)):
+                    # a looped-over array of a time-domain program: operations name it (blackbird keeps the name)
+                    prog.variables[m.group(1)] = np.atleast_2d(arr)
+                    env[m.group(1)] = Parameter.free(m.group(1))
+                else:
+                    env[m.group(1)] = arr
             else:
                 m = re.match(r"^([A-Za-z_]\w*)\s*=\s*(.+)$", rest)
                 if not m:
@@ -745,13 +760,15 @@ def _loads_xir(text):
                         val = v.strip().strip('"')
                     if kind == "options":
                         prog.options[k.strip()] = val
+                    elif str(prog.options.get("_type_", "")) == "tdm" and re.fullmatch(r"p\d+", k.strip()):
+                        prog.variables[k.strip()] = val      # looped-over array: statements keep the name
                     else:
                         env[k.strip()] = val
             text = text[:m.start()] + text[m.end():]
     if "_name_" in prog.options:
         prog.name = prog.options.pop("_name_")
-    if str(prog.options.get("_type_", "")).strip('"') == "tdm":
-        raise NotImplementedError("time-domain (tdm) XIR programs are not supported by the b200fock loader")
+    if str(prog.options.get("_type_", "")) == "tdm":
+        prog.programtype = {"name": "tdm", "options": {"N": prog.options.get("N")}}
 
     # gate definitions: ``gate Name(params)[wires]: <statements> end;`` (params and wires optional; wires default
     # to the labels of the body in sorted order).  Expanded in place at every use, as the reference does through
@@ -853,15 +870,25 @@ def _dumps_xir(prog):
 
 
 # ------------------------------------------------------------------------------------ public API (io/__init__.py)
+def _refuse_time_domain(prog):
+    if prog.programtype["name"] == "tdm":
+        raise NotImplementedError("time-domain (tdm) programs run on the reference's TDMProgram / hardware path, "
+                                  "not on the Fock backend (DESIGN section 8)")
+    if prog.programtype["name"] is not None:
+        raise NotImplementedError("Blackbird program type %r is not supported" % prog.programtype["name"])
+
+
 def loads(s, ir="blackbird"):
     """Load a circuit from a string (``sf.loads``, ``io/__init__.py:145-166``)."""
     if ir == "blackbird":
         prog = _loads_blackbird(s)
+        _refuse_time_domain(prog)
         if not prog.operations:     # io/__init__.py:50-53: the number of modes of an empty program is unknown
             raise ValueError("Blackbird program contains no quantum operations!")
         return prog
     if ir == "xir":
         prog = _loads_xir(s)
+        _refuse_time_domain(prog)
         if not prog.operations:     # xir_io.py:78-82
             raise ValueError("The XIR program is empty and cannot be transformed into a Strawberry Fields program.")
         return prog

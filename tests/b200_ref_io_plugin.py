@@ -1,7 +1,7 @@
 """pytest plugin (build container only): run the REFERENCE's own Blackbird I/O tests on ``strawberryfields_b200.io``.
 
     cd /tmp && PYTHONPATH=/root/repo:/root/repo/tests python -m pytest -p b200_ref_io_plugin -p no:cacheprovider \
-        /root/reference/tests/frontend/io -q -k "not tdm"
+        /root/reference/tests/frontend/io -q
 
 Installs the import shim for the absent third-party packages (oracle/ref_shim.py) and then replaces the inert
 ``blackbird`` / ``xir`` stand-ins by ``tests/blackbird_facade.py`` / ``tests/xir_facade.py``: the reference's ``sf.load`` / ``sf.save`` /

@@ -7,8 +7,9 @@ With this facade in ``sys.modules`` (``install()``; ``tests/b200_ref_io_plugin.p
 reference's conftest is imported) ``sf.load`` / ``sf.loads`` / ``sf.save`` / ``io.to_blackbird`` /
 ``io.to_program`` are the reference's unmodified code, and every Blackbird script they read or write goes
 through ``strawberryfields_b200.io`` -- which is what the reference's ``tests/frontend/io/test_io_blackbird.py``
-then checks.  Only the attributes the reference touches are provided.  Time-domain programs (``type tdm``)
-are out of scope: the facade raises ``NotImplementedError`` for them.
+then checks.  Only the attributes the reference touches are provided.  Time-domain programs (``type tdm``) are
+parsed (type line, looped-over arrays kept by name) so that the reference can convert them to its ``TDMProgram``;
+running them is out of scope and writing them raises ``NotImplementedError``.
 """
 import sys
 import types
@@ -104,12 +105,23 @@ def loads(text):
     prog = bio._loads_blackbird(text)
     bb = BlackbirdProgram(name=prog.name, version=prog.version)
     bb._target = {"name": prog.target.get("name"), "options": dict(prog.target.get("options", {}))}
+    bb._type = {"name": prog.programtype["name"], "options": dict(prog.programtype["options"])}
+    bb._var = dict(prog.variables)
+    tdm = bb._type["name"] == "tdm"
+
+    def conv(a):
+        # time-domain programs: blackbird hands the looped-over arrays to the converter by NAME
+        # (blackbird_io.py:100-108,130-137)
+        if tdm and isinstance(a, bio.Parameter) and a.node[0] == "free":
+            return a.node[1]
+        return _to_sympy(a)
+
     bare = getattr(prog, "_bare", set())
     for i, op in enumerate(prog.operations):
         entry = {"op": op["op"], "modes": list(op["modes"])}
         if i not in bare:   # ``Vac | 0`` carries no argument lists, ``Vacuum() | 0`` empty ones (blackbird_io.py:63-77)
-            entry["args"] = [_to_sympy(a) for a in op["args"]]
-            entry["kwargs"] = {k: _to_sympy(a) for k, a in op["kwargs"].items()}
+            entry["args"] = [conv(a) for a in op["args"]]
+            entry["kwargs"] = {k: conv(a) for k, a in op["kwargs"].items()}
         bb._operations.append(entry)
         bb._modes |= set(op["modes"])
     return bb

@@ -119,7 +119,8 @@ for int j in 0:6:2
 
 
 @pytest.mark.parametrize("bad,exc", [("Sgate(0.3 | 0", bio.ProgramSyntaxError), ("Sgate(foo) | 0", NameError),
-                                     ("type int x", NotImplementedError),
+                                     ("type tdm (temporal_modes=2)\nSgate(0.1, 0.0) | 0", NotImplementedError),
+                                     ("type tdm 3", bio.ProgramSyntaxError),
                                      ("include \"lib.xbb\"", NotImplementedError),
                                      ("Sgate(__import__('os')) | 0", bio.ProgramSyntaxError)])
 def test_bad_scripts_are_refused(bad, exc):

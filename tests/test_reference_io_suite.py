@@ -2,8 +2,8 @@
 ``sf.load`` / ``sf.loads`` / ``sf.save``, code generation, engine integration) run on ``strawberryfields_b200.io``:
 ``tests/b200_ref_io_plugin.py`` puts facades for the absent ``blackbird`` / ``xir`` packages into ``sys.modules``
 that parse and write every script with our module, while the conversion code under test is the reference's,
-unmodified.  Build container only (``/root/reference`` does not travel).  Time-domain (``tdm``) cases are
-deselected: out of scope."""
+unmodified.  Build container only (``/root/reference`` does not travel).  Time-domain (``tdm``) scripts are parsed
+for the reference's converter (type line, looped-over arrays by name); ``loads`` itself refuses to run them."""
 import os
 import re
 import subprocess
@@ -19,9 +19,9 @@ def test_reference_io_tests_pass_on_our_parsers(tmp_path):
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([ROOT, os.path.join(ROOT, "tests")]))
     res = subprocess.run(
         [sys.executable, "-m", "pytest", "-p", "b200_ref_io_plugin", "-p", "no:cacheprovider",
-         "/root/reference/tests/frontend/io", "-q", "-k", "not tdm"],
+         "/root/reference/tests/frontend/io", "-q"],
         cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=600)
     tail = res.stdout.strip().splitlines()[-1] if res.stdout.strip() else res.stderr[-400:]
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-1000:]
     m = re.search(r"(\d+) passed", tail)
-    assert m and int(m.group(1)) >= 90 and "failed" not in tail, tail
+    assert m and int(m.group(1)) >= 100 and "failed" not in tail, tail

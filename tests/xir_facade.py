@@ -5,7 +5,8 @@ The reference converts programs through ``xir.Program`` / ``xir.Statement`` / ``
 scripts with ``xir.parse_script`` (``strawberryfields/io/xir_io.py:33-330``, ``io/__init__.py:145-237``).  Here
 the containers are plain classes with the attributes the reference touches; ``parse_script`` and
 ``Program.serialize`` go through our XIR parser / writer (gate definitions are already expanded by the parser,
-so ``Program.gates`` is empty).  Time-domain programs (``_type_: tdm``) are out of scope.
+so ``Program.gates`` is empty).  Time-domain programs (``_type_: tdm``) are parsed (looped-over arrays kept by name)
+for the reference's converter; running or writing them is out of scope.
 """
 import sys
 import types
@@ -105,6 +106,8 @@ def parse_script(script, eval_pi=False, use_floats=True, **kwargs):
         out.add_option("_name_", prog.name)
     for k, v in prog.options.items():
         out.add_option(k, v)
+    for k, v in prog.variables.items():     # time-domain programs: the looped-over arrays (xir_io.py:160-170)
+        out.add_constant(k, v)
     for op in prog.operations:
         params = {k: _plain(v) for k, v in op["kwargs"].items()} if op["kwargs"] else [_plain(a) for a in op["args"]]
         out.add_statement(Statement(op["op"], params, tuple(op["modes"])))
