@@ -764,8 +764,8 @@ def main():
     ap.add_argument("--parity-probs", type=int, default=1000, help="sharded arm: Fock probabilities compared")
     ap.add_argument("--no-ten-mode", action="store_true", help="8-GPU sharded arm: skip the 10-mode / 160 GB block")
     ap.add_argument("--from-vacuum", action="store_true",
-                    help="every step resets to vacuum first and uses the lazy-vacuum option (not yet the default: "
-                         "unmeasured in round 1)")
+                    help="the device-timed step starts from vacuum with the plugin's default lazy vacuum (reset + "
+                         "gates + flush) instead of re-applying the gates to the dense state of the previous step")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
