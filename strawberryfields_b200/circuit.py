@@ -1249,7 +1249,7 @@ class DeviceCircuit:
         sb = (lambda per: per) if per_entry else (lambda per: 0)    # stride of the batch axis in the new state
         per = self._size()
 
-        def finish(out, pure, touched=True):
+        def finish(out, touched=True):
             self._buf, self._shared, self._scratch = out, False, None
             if touched:
                 self._touch(*modes)
@@ -1268,7 +1268,7 @@ class DeviceCircuit:
                     src_axis = j if self._pure else 2 * j + t
                     oa.append((D, D ** (naxes - 1 - src_axis), 0, self._stride(ax)))
             self._gather(src, None, out, oa)
-            finish(out, is_ket, touched=False)
+            finish(out, touched=False)
             self._untouched = set()
             return
 
@@ -1283,7 +1283,7 @@ class DeviceCircuit:
                 else:
                     oa.append((D, self._stride(f), 0, self._stride(f)))
             self._gather(self._buf, src, out, oa)
-            finish(out, True)
+            finish(out)
             return
 
         # general case: rho_b <- Tr_modes(rho_b) (x) new_b
@@ -1310,7 +1310,7 @@ class DeviceCircuit:
                     j = keep.index(f)
                     oa.append((D, D ** (2 * kk - 1 - (2 * j + t)), 0, sc))
         self._gather(red, src, out, oa)
-        finish(out, False)
+        finish(out)
 
     def prepare(self, state, mode):
         self.prepare_multimode(state, [mode] if isinstance(mode, int) else mode)
